@@ -1,0 +1,204 @@
+"""Deterministic definitions of the golden / parity cases.
+
+Shared by ``make_golden.py`` (which runs the unmodified reference in the build
+container), the ``not gpu`` oracle-pinning tests and the ``gpu`` parity tests.
+Everything here is regenerated from seeds; only the reference's *outputs* are
+stored in ``tests/golden/*.npz``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import stnerf_oracle as O  # noqa: E402
+
+GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
+CKPT_DIRS = [os.path.join(ROOT, "oracle", "_ref", "ckpt"), "/root/reference/outputs"]
+
+# name -> spec.  weights: "taekwondo" | "walking" (shipped checkpoints) | "synthetic"
+CASES = {
+    # BASELINE config #1 flavour: 1 performer, coarse only, 64 samples
+    "syn_L1_coarse": dict(weights="synthetic", seed=11, L=1, space_time=True, n1=64, n2=0, only_coarse=True,
+                          frame_ids=[0, 10], thr=(1e-4, 0.0), n_rays=160, ray_seed=1),
+    "syn_L2_64_128": dict(weights="synthetic", seed=12, L=2, space_time=True, n1=64, n2=128,
+                          frame_ids=[0, 10, 11], thr=(0.0, 0.0), n_rays=160, ray_seed=2),
+    # the demo configuration of taekwondo (thresholds 0/0), integer frame ids
+    "tkd_64_128": dict(weights="taekwondo", L=2, space_time=True, n1=64, n2=128,
+                       frame_ids=[0, 10, 11], thr=(0.0, 0.0), n_rays=192, ray_seed=3),
+    # fractional frame ids (MotionNet lerp + bbox lerp) and the shift/scale edits of demo/taekwondo_demo.py:55,65
+    "tkd_edit_frac": dict(weights="taekwondo", L=2, space_time=True, n1=64, n2=128,
+                          frame_ids=[0, 10.5, 11.25], thr=(1e-4, 0.0), n_rays=192, ray_seed=4,
+                          shift=[[0, 0, 0], [0, 2, 0], [0, -2, 0]], scale=[1, 0.75, 1.5], alpha=0.5),
+    # demo/walking_demo.py:43-50: thresholds 20/0.8, near=4; reference sample counts 90+30; layer 1 hidden
+    "walk_90_30_hide": dict(weights="walking", L=2, space_time=False, n1=90, n2=30,
+                            frame_ids=[0, 30, 31], thr=(20.0, 0.8), near=4.0, hidden=[1], n_rays=160, ray_seed=5),
+    # BASELINE config #3 flavour: walking nets replicated round-robin to 4 performer layers
+    "walk_L4_64_128": dict(weights="walking", L=4, space_time=False, n1=64, n2=128,
+                           frame_ids=[0, 30, 31, 32, 33], thr=(20.0, 0.8), near=4.0, n_rays=128, ray_seed=6),
+}
+
+
+def find_checkpoint(scene: str):
+    for d in CKPT_DIRS:
+        for p in (os.path.join(d, scene + ".pt"), os.path.join(d, scene, "layered_rfnr_checkpoint_1.pt")):
+            if os.path.isfile(p):
+                return p
+    return None
+
+
+def replicate_layers(sd: dict, L: int) -> dict:
+    """configs with more performers than the checkpoint reuse its nets round-robin."""
+    have = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("spacenets."))
+    out = {k: v for k, v in sd.items() if k.startswith("bkgd_")}
+    for i in range(L):
+        for grp in ("spacenets", "spacenets_fine", "time_deform_nets"):
+            src = "%s.%d." % (grp, i % have)
+            for k, v in sd.items():
+                if k.startswith(src):
+                    out["%s.%d.%s" % (grp, i, k[len(src):])] = v
+    return out
+
+
+def state_dict_for(case: dict):
+    """Returns the fp32 state_dict of the case, or None when it needs a checkpoint that is not present."""
+    if case["weights"] == "synthetic":
+        return O.synthetic_state_dict(case["L"], case["space_time"], seed=case["seed"])
+    path = find_checkpoint(case["weights"])
+    if path is None:
+        return None
+    sd = torch.load(path, map_location="cpu")
+    sd = sd["model"] if "model" in sd else sd
+    return replicate_layers(sd, case["L"])
+
+
+def boxes_for(case: dict):
+    return O.synthetic_boxes(case["L"])
+
+
+def rays_for(case: dict) -> torch.Tensor:
+    """n_rays rays from the 1080p synthetic camera (view 1 of 16) + frame-id columns.
+
+    A quarter are pixel-grid rays (incl. the four image corners, which miss every performer);
+    the rest are aimed at random points in and just around each (edited) performer box so that
+    every layer gets hits, grazing rays and near misses.
+    """
+    K, T = O.synthetic_camera(1, 16, 1080, 1920)
+    rs = np.random.RandomState(case["ray_seed"])
+    n = case["n_rays"]
+    n_grid = n // 4
+    rows = rs.randint(250, 900, size=n_grid)
+    cols = rs.randint(350, 1570, size=n_grid)
+    rows[:4], cols[:4] = [0, 0, 1079, 1079], [0, 1919, 0, 1919]
+    full = O.generate_rays(K, T, 1080, 1920)
+    grid = full[torch.from_numpy(rows * 1920 + cols)]
+    sc = scene_for(case)
+    eye = T[:3, 3]
+    aimed = []
+    L = case["L"]
+    for j in range(n - n_grid):
+        i = 1 + (j % L)
+        lo, hi = sc["bmin"][i], sc["bmax"][i]
+        c, half = (lo + hi) / 2, (hi - lo) / 2
+        p = c + half * 1.25 * torch.from_numpy(rs.uniform(-1, 1, 3).astype(np.float32))
+        dvec = p - eye
+        aimed.append(torch.cat([eye, dvec / dvec.norm()]))
+    rays = torch.cat([grid, torch.stack(aimed, 0)], 0)
+    fid = torch.tensor(case["frame_ids"], dtype=torch.float32)[None].expand(n, -1)
+    return torch.cat([rays, fid], 1).contiguous()
+
+
+def uniforms_for(case: dict):
+    l = case["L"] + 1
+    rs = np.random.RandomState(1000 + case["ray_seed"])
+    jit = torch.from_numpy(rs.random_sample((l, case["n_rays"], case["n1"])).astype(np.float32))
+    u = torch.from_numpy(rs.random_sample((l, case["n_rays"], max(case["n2"], 1))).astype(np.float32))
+    # float32 rounding of a double in [0,1) can give exactly 1.0; torch.rand never does
+    jit.clamp_(max=float(np.nextafter(np.float32(1), np.float32(0))))
+    u.clamp_(max=float(np.nextafter(np.float32(1), np.float32(0))))
+    return jit, (u if case["n2"] > 0 else None)
+
+
+def scene_for(case: dict):
+    """Oracle-side scene dict (edited boxes etc.) for the case."""
+    bkgd, frames = boxes_for(case)
+    sc = O.resolve_scene(frames, bkgd, case["frame_ids"], case.get("scale"), case.get("shift"))
+    l = case["L"] + 1
+    sc.update(scale=case.get("scale"), shift=case.get("shift"),
+              shown=[i not in case.get("hidden", []) for i in range(l)],
+              near=case.get("near", 0.0), alpha=case.get("alpha", 1.0), boarder=1e10)
+    return sc
+
+
+OUTPUT_KEYS = ("fine_mixed", "coarse_mixed", "fine_layer", "coarse_layer")
+
+
+def flatten_outputs(fine_mixed, coarse_mixed, fine_layer, coarse_layer, ray_mask) -> dict:
+    """5-tuple of the reference / facade -> flat dict of numpy arrays (the .npz schema)."""
+    d = {}
+    for name, trip in (("fine_mixed", fine_mixed), ("coarse_mixed", coarse_mixed)):
+        for part, v in zip(("rgb", "depth", "acc"), trip):
+            d["%s.%s" % (name, part)] = np.asarray(v.detach().cpu().reshape(v.shape[0], -1), dtype=np.float32)
+    for name, lst in (("fine_layer", fine_layer), ("coarse_layer", coarse_layer)):
+        for i, trip in enumerate(lst):
+            for part, v in zip(("rgb", "depth", "acc"), trip):
+                d["%s.%d.%s" % (name, i, part)] = np.asarray(v.detach().cpu().reshape(v.shape[0], -1), dtype=np.float32)
+    for i, m in enumerate(ray_mask):
+        d["ray_mask.%d" % i] = np.asarray(m.detach().cpu()).astype(np.uint8)
+    return d
+
+
+def load_golden(name: str):
+    p = os.path.join(GOLDEN_DIR, name + ".npz")
+    return dict(np.load(p)) if os.path.isfile(p) else None
+
+
+# --------------------------------------------------------------------------- per-function vectors
+def function_inputs() -> dict:
+    """Seeded inputs for the per-stage goldens (functions.npz).  Pure function of the seeds below."""
+    rs = np.random.RandomState(77)
+    f = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))  # noqa: E731
+    uni = lambda *s: torch.from_numpy(rs.random_sample(s).astype(np.float32)).clamp_(max=0.99999994)  # noqa: E731
+    d = {}
+    # rays around two boxes (some start inside, some miss, some axis-parallel)
+    n = 256
+    o = f(n, 3) * 2.0
+    dirs = f(n, 3)
+    dirs = dirs / dirs.norm(dim=1, keepdim=True)
+    dirs[:8, 0] = 0.0            # exactly axis-parallel components (the +eps branch)
+    o[8:16] = o[8:16] * 0.2      # origins inside the box
+    d["isect.rays"] = torch.cat([o, dirs], 1)
+    d["isect.bmin"] = torch.tensor([-1.0, -0.5, -0.25])
+    d["isect.bmax"] = torch.tensor([1.0, 0.75, 1.5])
+    d["sample.jitter"] = uni(2, n, 48)
+    # compositing
+    t = torch.sort(uni(64, 96) * 6.0, 1)[0]
+    d["comp.t"] = t
+    d["comp.rgb"] = f(64, 96, 3) * 3.0
+    d["comp.sigma"] = f(64, 96) * 40.0
+    # sample_pdf
+    d["pdf.t"] = torch.sort(uni(64, 64) * 5.0 + 1.0, 1)[0]
+    w = uni(64, 64) ** 8
+    w[:4] = 0.0                  # all-zero weights -> uniform pdf
+    w[4:8, 10] = 50.0            # one dominant bin
+    d["pdf.w"] = w
+    d["pdf.u"] = uni(64, 128)
+    # encodings / nets
+    d["pe.x3"] = f(200, 3) * 3.0
+    d["pe.x1"] = uni(50, 1) * 100.0
+    d["net.pos"] = f(300, 3) * 1.5
+    dd = f(300, 3)
+    d["net.dirs"] = dd / dd.norm(dim=1, keepdim=True)
+    d["net.time_int"] = torch.full((300, 1), 37.0)
+    d["net.time_frac"] = torch.full((300, 1), 37.25)
+    # ray generation: a small image with an off-centre principal point
+    d["rays.K"] = torch.tensor([[31.2, 0.0, 19.5], [0.0, 30.7, 12.25], [0.0, 0.0, 1.0]])
+    K, T = O.synthetic_camera(3, 16, 24, 40)
+    d["rays.T"] = T
+    return d

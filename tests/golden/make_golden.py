@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running the UNMODIFIED reference on CPU.
+
+Run in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py            # all cases + functions.npz
+    python tests/golden/make_golden.py tkd_64_128 # one case
+
+Also refreshes ``oracle/_ref/ckpt/*.pt`` (git-ignored copies of the shipped
+checkpoints -- weights are input data, not source -- so the GPU box, which has no
+/root/reference, can run the checkpoint parity cases).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import cases as C  # noqa: E402
+from oracle import reference_shim as R  # noqa: E402
+
+
+def stash_checkpoints():
+    dst = os.path.join(C.ROOT, "oracle", "_ref", "ckpt")
+    os.makedirs(dst, exist_ok=True)
+    for scene in ("taekwondo", "walking"):
+        src = os.path.join(R.REFERENCE_ROOT, "outputs", scene, "layered_rfnr_checkpoint_1.pt")
+        out = os.path.join(dst, scene + ".pt")
+        if os.path.isfile(src) and not os.path.isfile(out):
+            shutil.copyfile(src, out)
+
+
+def run_case(name: str):
+    case = C.CASES[name]
+    sd = C.state_dict_for(case)
+    bkgd, frames = C.boxes_for(case)
+    model = R.build_model(sd, case["L"], case["n1"], case["n2"], case["space_time"], bkgd, frames,
+                          scale=case.get("scale"), shift=case.get("shift"))
+    model.near = case.get("near", 0.0)
+    model.alpha = case.get("alpha", 1.0)
+    for i in case.get("hidden", []):
+        model.hide_layer(i)
+    rays = C.rays_for(case)
+    jit, u = C.uniforms_for(case)
+    t0 = time.time()
+    out = R.forward(model, rays, jit, u, only_coarse=case.get("only_coarse", False),
+                    density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+    dt = time.time() - t0
+    flat = C.flatten_outputs(*out)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **flat)
+    hits = [int(m.sum()) for m in out[4]]
+    print("%-18s %4d rays  %.2fs  hits=%s" % (name, rays.shape[0], dt, hits))
+
+
+def run_functions():
+    m = R.modules()
+    from layers.RaySamplePoint import intersection, RaySamplePoint
+    from layers.render_layer import VolumeRenderer
+    from utils.sample_pdf import sample_pdf
+    from utils.dimension_kernel import Trigonometric_kernel
+    from utils.render_helpers import generate_rays
+    from modeling.spacenet import SpaceNet
+    from modeling.motion_net import MotionNet
+    import contextlib, io
+
+    d = C.function_inputs()
+    out = {}
+    n = d["isect.rays"].shape[0]
+    bbox = C.O.corners_from_minmax(d["isect.bmin"], d["isect.bmax"])[None].expand(n, 8, 3)
+    out["isect.t"] = intersection(d["isect.rays"], bbox)
+    # RaySamplePoint over two layers (layer 0 = bkgd clamp branch) with injected jitter
+    rsp = RaySamplePoint(48)
+    with R.injected_uniforms([d["sample.jitter"][0], d["sample.jitter"][1]]):
+        ts, xyz, mask = rsp.forward(d["isect.rays"], torch.stack([bbox, bbox], 1))
+    for i in range(2):
+        out["sample.t.%d" % i], out["sample.xyz.%d" % i], out["sample.mask.%d" % i] = ts[i][..., 0], xyz[i], mask[i].to(torch.uint8)
+    vr = VolumeRenderer(boarder_weight=1e10)
+    c, dp, a, w = vr(d["comp.t"][..., None], d["comp.rgb"], d["comp.sigma"][..., None])
+    out["comp.color"], out["comp.depth"], out["comp.acc"], out["comp.w"] = c, dp, a, w[..., 0]
+    with R.injected_uniforms([d["pdf.u"]]):
+        out["pdf.z"] = sample_pdf(d["pdf.t"], d["pdf.w"][:, 1:-1], N_samples=d["pdf.u"].shape[1])
+    out["pe.x3_L10"] = Trigonometric_kernel(L=10)(d["pe.x3"])
+    out["pe.x3_L4"] = Trigonometric_kernel(L=4)(d["pe.x3"])
+    out["pe.x1_L10"] = Trigonometric_kernel(L=10, input_dim=1)(d["pe.x1"])
+    with R.cpu_cuda_shim():
+        rays, _ = generate_rays(d["rays.K"], d["rays.T"], None, 24, 40)
+    out["rays.rays"] = rays
+    # networks: seeded synthetic weights always; checkpoint nets when present
+    def space(sd_prefix, sd, use_time):
+        net = SpaceNet(include_input=True, use_dir=True, use_time=use_time)
+        net.load_state_dict({k[len(sd_prefix):]: v for k, v in sd.items() if k.startswith(sd_prefix)})
+        with torch.no_grad():
+            return net(d["net.pos"], torch.cat([d["net.pos"], d["net.dirs"]], 1), d["net.time_int"])
+
+    def motion(sd_prefix, sd, tcol):
+        net = MotionNet(include_input=True, c_input=4, input_time=True)
+        net.load_state_dict({k[len(sd_prefix):]: v for k, v in sd.items() if k.startswith(sd_prefix)})
+        with torch.no_grad():
+            return net(torch.cat([d["net.pos"], tcol], 1))
+
+    srcs = {"syn": C.O.synthetic_state_dict(1, True, seed=5)}
+    if R.available():
+        srcs["tkd"] = R.load_checkpoint("taekwondo")
+        srcs["walk"] = R.load_checkpoint("walking")
+    for tag, sd in srcs.items():
+        ut = sd["spacenets.0.rgb_net.1.weight"].shape[1] == 304
+        r, s = space("spacenets.0.", sd, ut)
+        out["net.%s.perf.rgb" % tag], out["net.%s.perf.sigma" % tag] = r, s
+        r, s = space("bkgd_spacenet_fine.", sd, False)
+        out["net.%s.bkgd.rgb" % tag], out["net.%s.bkgd.sigma" % tag] = r, s
+        out["net.%s.motion_int" % tag] = motion("time_deform_nets.0.", sd, d["net.time_int"])
+        out["net.%s.motion_frac" % tag] = motion("time_deform_nets.0.", sd, d["net.time_frac"])
+    np.savez_compressed(os.path.join(HERE, "functions.npz"),
+                        **{k: np.asarray(v.detach()) for k, v in out.items()})
+    print("functions.npz: %d arrays" % len(out))
+
+
+if __name__ == "__main__":
+    assert R.available(), "needs /root/reference (build container only)"
+    torch.set_num_threads(os.cpu_count())
+    stash_checkpoints()
+    names = sys.argv[1:] or (list(C.CASES) + ["functions"])
+    for nm in names:
+        if nm == "functions":
+            run_functions()
+        else:
+            run_case(nm)
