@@ -1,0 +1,168 @@
+/*
+ * stnerf.h -- C ABI of libstnerf_b200.so: the st-nerf layered ray-march hot path on B200 (sm_100a).
+ *
+ * The reference (DarlingHang/st-nerf) has no FFI seam: its boundary is the Python call surface
+ *   modeling/layered_rfrender.py:141   LayeredRFRender.forward(rays, labels, bboxes, only_coarse, ...)
+ *   utils/batchify_rays.py:51          layered_batchify_ray(model, rays, ...)
+ *   engine/render.py:30                render(model, K, T, img_size, ...)
+ * The Python facade in st-nerf_b200/{modeling,utils,layers,engine} keeps that surface and marshals it
+ * onto the entry points below through ctypes.  Each entry point cites the reference
+ * code it replaces.  Paths are relative to the reference root.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all functions return 0 on success or a negative STNERF_E* code; nothing throws; no hidden
+ *     synchronisation: work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - the context owns its weights and a workspace; the workspace is (re)allocated only when a call
+ *     asks for more rays-per-chunk / samples than any previous call (stnerf_reserve does it up front);
+ *   - there is no CPU fallback: without a CUDA device every call returns STNERF_ENODEVICE.
+ */
+#ifndef STNERF_H_
+#define STNERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STNERF_MAX_LAYERS 8      /* l = 1 background + up to 7 performers (BASELINE config #5 uses 7) */
+#define STNERF_MAX_N1 128        /* coarse samples per ray per layer                                  */
+#define STNERF_MAX_S 512         /* n1 + n2                                                           */
+
+enum {
+  STNERF_OK = 0,
+  STNERF_EINVAL = -1,      /* bad argument (the reference prints + exit(-1), layered_rfrender.py:162) */
+  STNERF_ENODEVICE = -2,   /* no CUDA device / wrong architecture                                    */
+  STNERF_ECUDA = -3,       /* a CUDA runtime call failed; stnerf_last_cuda_error() has the text      */
+  STNERF_ENOWEIGHTS = -4,  /* a network needed by the call was never loaded                          */
+  STNERF_ENOMEM = -5
+};
+
+/* Arithmetic mode of the two MLPs (modeling/spacenet.py:101-160, modeling/motion_net.py:34-71). */
+enum {
+  STNERF_PREC_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores: the bit-closest mode, validation baseline      */
+  STNERF_PREC_TC_3XF16 = 1,    /* tcgen05 fp16 3-term split (hi*hi + lo*hi + hi*lo), fp32 accumulate:     */
+                               /* ~fp32 products, meets the 1e-3 RGB gate               */
+  STNERF_PREC_TC_F16 = 2       /* tcgen05 single fp16 pass: fastest, does NOT meet the 1e-3 gate          */
+};
+
+typedef struct stnerf_ctx* stnerf_handle;
+
+typedef struct {
+  int32_t n_layers;                              /* l = L+1, layer 0 = background (layered_rfrender.py:56,209) */
+  int32_t space_time[STNERF_MAX_LAYERS];         /* net of layer i consumes PE(time) in its rgb head           */
+                                                 /* (cfg.MODEL.USE_SPACE_TIME, layered_rfrender.py:62-67)       */
+  int32_t precision;                             /* STNERF_PREC_*                                               */
+  int32_t chunk_rays;                            /* rays per internal chunk; 0 = default (65536)                */
+} stnerf_model_desc;
+
+/* Per-call scene constants: what LayeredRFRender.forward derives in its prologue
+ * (layered_rfrender.py:190-242) plus the attributes the renderer mutates between frames
+ * (render/layered_neural_renderer.py:435-440).  All host memory. */
+typedef struct {
+  float bmin[STNERF_MAX_LAYERS][3];              /* box corner 0 after scale/shift edits (:230-242)             */
+  float bmax[STNERF_MAX_LAYERS][3];              /* box corner 6 after edits                                    */
+  int32_t shown[STNERF_MAX_LAYERS];              /* display_layers (:104-112); entry 0 is ignored like the ref. */
+  /* inverse edit applied to sample points before the nets: p -= shift; p = (p - pivot)/scale + pivot           */
+  int32_t shift_on[STNERF_MAX_LAYERS];           /* (:293-298) == (:467-471)                                    */
+  float shift[STNERF_MAX_LAYERS][3];
+  int32_t scale_coarse_on[STNERF_MAX_LAYERS];    /* (:300-303)                                                  */
+  int32_t scale_fine_on[STNERF_MAX_LAYERS];      /* (:473-475), skipped when that layer's shift entry is None   */
+  float scale[STNERF_MAX_LAYERS];
+  float pivot[3];                                /* (centre_layer2 + centre_layer1)/2 (:221-232)                */
+  float near_plane;                              /* model.near (:143,422,605)                                   */
+  float alpha_layer2;                            /* model.alpha, fine pass, layer 2 only (:575-576)             */
+  float density_threshold;                       /* (:416-418, 564-566)                                         */
+  float bkgd_density_threshold;                  /* (:538-547)                                                  */
+  float boarder_weight;                          /* cfg.MODEL.BOARDER_WEIGHT, last delta (render_layer.py:38)   */
+  int32_t apply_thresholds;                      /* 1 in the retiming branch (:416,538,564), else 0             */
+} stnerf_scene;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int stnerf_create(stnerf_handle* out, const stnerf_model_desc* desc_host);   /* modeling/__init__.py:5-7 build_layered_model */
+void stnerf_destroy(stnerf_handle h);
+int stnerf_reserve(stnerf_handle h, int n1, int n2);                         /* size the workspace up front                  */
+size_t stnerf_workspace_bytes(stnerf_handle h);
+const char* stnerf_strerror(int code);
+const char* stnerf_last_cuda_error(void);
+int stnerf_set_precision(stnerf_handle h, int precision);
+
+/* ---- weights: load_state_dict (render/layered_neural_renderer.py:110-117) ------------------------------ */
+/* blob = the net's tensors concatenated in state_dict order, fp32, nn.Linear (out,in) row-major:
+ *   SpaceNet : stage1.{0,2,4,6}.{weight,bias}, stage2.{0,2,4}.{weight,bias}, density_net.0.{weight,bias},
+ *              rgb_net.1.{weight,bias}, rgb_net.3.{weight,bias}      (464260 or 466948 floats)
+ *   MotionNet: motion_net.{0,2,4,6,8,10}.{weight,bias}               (77315 floats)
+ * layer 0 = background; fine = 0 coarse net / 1 fine net.  MotionNets are shared by both passes.        */
+int stnerf_load_spacenet(stnerf_handle h, int layer, int fine, const float* blob_host, size_t n_floats);
+int stnerf_load_motionnet(stnerf_handle h, int layer, const float* blob_host, size_t n_floats);
+
+int stnerf_set_scene(stnerf_handle h, const stnerf_scene* scene_host);
+
+/* ---- the hot path: LayeredRFRender.forward (layered_rfrender.py:141-734), BBOX sampling ---------------- */
+/* rays: (n_rays, ray_stride) fp32, columns [o(3), d(3), frame_id_layer0 .. frame_id_layer(l-1)]
+ *       (data/datasets/ray_dataset.py:276-281); ray_stride >= 6 + l.
+ * jitter: (l, n_rays, n1) uniforms for layers/RaySamplePoint.py:98, or NULL -> in-kernel Philox(seed).
+ * u:      (l, n_rays, n2) uniforms for utils/sample_pdf.py:31, or NULL -> Philox(seed).
+ * out:    [2 passes: 0 coarse, 1 fine][l+1 images: 0 mixed, 1+i layer i] planes of 5*n_rays floats each,
+ *         a plane = rgb (n_rays,3) | depth (n_rays) | acc (n_rays)   (the tuples of :725-734).
+ *         With only_coarse the fine planes are left untouched (the facade aliases them, :721-722).
+ * ray_mask: (l, n_rays) uint8, |bin_width| > 1e-5 (layers/RaySamplePoint.py:105).                        */
+int stnerf_render(stnerf_handle h, const float* rays, int64_t n_rays, int ray_stride, int n1, int n2,
+                  int only_coarse, const float* jitter, const float* u, uint64_t seed,
+                  float* out, uint8_t* ray_mask, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of rays, render, D2H of out/ray_mask on `stream`,
+ * returns after the stream has drained.  This is the e2e path bench.py times.                             */
+int stnerf_render_host(stnerf_handle h, const float* rays_host, int64_t n_rays, int ray_stride, int n1, int n2,
+                       int only_coarse, uint64_t seed, float* out_host, uint8_t* ray_mask_host, void* stream);
+
+/* ---- ray generation: utils/render_helpers.py:96-123 == utils/ray_sampling.py:22-72 --------------------- */
+/* Kinv_host = inverse(K) (3x3 row-major), T_host = camera-to-world (4x4 row-major).  Writes rows
+ * row0, row0+row_step, ... (n_rows of them) of an HxW image: rays[(k*W + j)*ray_stride + 0..5] = o,d and
+ * columns 6..6+n_frame_ids-1 = frame_ids_host (data/datasets/ray_dataset.py:276-281).                     */
+int stnerf_raygen(const float* Kinv_host, const float* T_host, int H, int W, int row0, int row_step, int n_rows,
+                  const float* frame_ids_host, int n_frame_ids, float* rays, int ray_stride, void* stream);
+
+/* ---- per-stage entry points (unit parity against the reference function named) ------------------------ */
+/* layers/RaySamplePoint.py:8-62 + :85-105 for one box.  t (n,n1), xyz (n,n1,3) or NULL, mask (n) uint8,
+ * tfar_tnear (n,2) or NULL = intersection()'s return.                                                     */
+int stnerf_intersect_sample(const float* rays, int64_t n, int ray_stride, const float* bmin_host,
+                            const float* bmax_host, int is_bkgd, int n1, const float* jitter,
+                            float* t, float* xyz, uint8_t* mask, float* tfar_tnear, void* stream);
+/* layers/render_layer.py:25-58.  t (n,S), rgb (n,S,3), sigma (n,S) -> color (n,3), depth (n), acc (n), w (n,S)|NULL */
+int stnerf_composite(const float* t, const float* rgb, const float* sigma, int64_t n, int S, float boarder,
+                     float* color, float* depth, float* acc, float* w, void* stream);
+/* utils/sample_pdf.py:18-63 (+ the sort of layered_rfrender.py:462 when t_fine != NULL).
+ * t (n,n1), w (n,n1) full weights (the [1:-1] slice is taken inside), u (n,n2) -> z (n,n2)|NULL, t_fine (n,n1+n2)|NULL */
+int stnerf_sample_pdf(const float* t, const float* w, const float* u, int64_t n, int n1, int n2,
+                      float* z, float* t_fine, void* stream);
+/* utils/dimension_kernel.py:24-33.  x (P,dim) -> out (P, dim*(1+2*n_freq)) */
+int stnerf_positional_encoding(const float* x, int64_t P, int dim, int n_freq, float* out, void* stream);
+/* modeling/spacenet.py:101-160.  pos (P,3), dirs (P,3), times (P)|NULL -> rgb (P,3) raw, sigma (P) raw */
+int stnerf_spacenet(stnerf_handle h, int layer, int fine, const float* pos, const float* dirs, const float* times,
+                    int64_t P, float* rgb, float* sigma, void* stream);
+/* modeling/motion_net.py:34-71.  xyzt (P,4) -> flow (P,3).  lerp_mode: -1 = decide like the reference
+ * (any non-integer t in the batch, :53), 0/1 = force.                                                      */
+int stnerf_motionnet(stnerf_handle h, int layer, const float* xyzt, int64_t P, int lerp_mode, float* flow,
+                     void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+uint64_t stnerf_launch_count(void);
+
+/* ---- measurement: per-kernel-class device times taken with CUDA events on the launching stream ----------- */
+/* classes: 0 SpaceNet MLP, 1 MotionNet MLP, 2 sampling, 3 compositing/resampling.  `points` = network
+ * evaluations (classes 0,1) or rays (2) / ray-passes (3) processed, so callers can turn ms into FLOP/s or B/s. */
+typedef struct {
+  double ms[4];
+  double points[4];
+  uint64_t launches[4];
+} stnerf_profile;
+int stnerf_profile_begin(stnerf_handle h);                       /* start recording (adds two events per launch)   */
+int stnerf_profile_end(stnerf_handle h, stnerf_profile* out_host); /* drain the device, stop recording, return totals */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STNERF_H_ */

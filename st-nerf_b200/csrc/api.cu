@@ -1,0 +1,544 @@
+// C ABI of libstnerf_b200 (include/stnerf.h): context, weight packing, workspace, chunked render orchestration.
+//
+// The orchestration restates the control flow of modeling/layered_rfrender.py:141-734 (BBOX sampling) as a
+// stream-ordered sequence of kernels per chunk of rays -- no host synchronisation, hit counts stay on the device:
+//   sample -> [bkgd SpaceNet] -> per performer [MotionNet -> SpaceNet] -> composite+resample
+//          -> same nets (fine weights) on n1+n2 depths -> per-layer + merged composite.
+#include <algorithm>
+#include <new>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+#include "mlp_tc.cuh"
+
+namespace stnerf {
+thread_local char g_cuda_err[512] = "";
+unsigned long long g_launches = 0;
+}  // namespace stnerf
+
+using namespace stnerf;
+
+namespace {
+
+struct SpaceNetDev {
+  float* blob = nullptr;       // SIMT layout (transposed fp32)
+  SpaceNetW w{};
+  TcNet tc{};                  // tcgen05 packing (mlp_tc.cu)
+  bool loaded = false;
+};
+struct MotionNetDev {
+  float* blob = nullptr;
+  MotionNetW w{};
+  TcNet tc{};
+  bool loaded = false;
+};
+
+}  // namespace
+
+struct stnerf_ctx {
+  stnerf_model_desc desc{};
+  int l = 0, num_sms = 0, device = 0, precision = 0, chunk_rays = 65536;
+  SpaceNetDev space[2][STNERF_MAX_LAYERS];
+  MotionNetDev motion[STNERF_MAX_LAYERS];
+  stnerf_scene scene{};
+  DevScene dscene{};
+  bool have_scene = false;
+  // workspace (sized for chunk_rays rays, cap_n1 coarse and cap_s2 total samples)
+  int cap_n1 = 0, cap_s2 = 0;
+  float *t_coarse = nullptr, *raw_coarse = nullptr, *t_fine = nullptr, *raw_fine = nullptr, *xyz = nullptr;
+  uint8_t* mask_ws = nullptr;
+  int *hit = nullptr, *counts = nullptr, *lerp_flags = nullptr;
+  size_t ws_bytes = 0;
+  // staging for stnerf_render_host
+  float *h_rays = nullptr, *h_out = nullptr;
+  uint8_t* h_mask = nullptr;
+  size_t h_rays_bytes = 0, h_out_bytes = 0, h_mask_bytes = 0;
+  int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
+  // profiling (stnerf_profile_begin / _end): CUDA-event pairs around every launch, on the launching stream
+  struct ProfRec { int cls; cudaEvent_t a, b; double points; int count_slot; int S; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  int* prof_counts = nullptr;  // pinned host copies of the per-chunk hit counts
+  int prof_chunks = 0;
+};
+
+namespace {
+constexpr int PROF_MAX_CHUNKS = 1 << 16;
+struct ProfScope {
+  stnerf_ctx* c; int idx = -1; cudaStream_t st;
+  ProfScope(stnerf_ctx* c_, int cls, double points, int count_slot, int S, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->prof_on) return;
+    stnerf_ctx::ProfRec r{cls, nullptr, nullptr, points, count_slot, S};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof[idx].b, st); }
+};
+}  // namespace
+
+static void free_ws(stnerf_ctx* c) {
+  cudaFree(c->t_coarse); cudaFree(c->raw_coarse); cudaFree(c->t_fine); cudaFree(c->raw_fine); cudaFree(c->xyz);
+  cudaFree(c->mask_ws); cudaFree(c->hit); cudaFree(c->counts); cudaFree(c->lerp_flags);
+  c->t_coarse = c->raw_coarse = c->t_fine = c->raw_fine = c->xyz = nullptr;
+  c->mask_ws = nullptr; c->hit = c->counts = c->lerp_flags = nullptr;
+  c->ws_bytes = 0; c->cap_n1 = c->cap_s2 = 0;
+}
+
+static int ensure_ws(stnerf_ctx* c, int n1, int s2) {
+  if (n1 <= c->cap_n1 && s2 <= c->cap_s2 && c->t_coarse) return STNERF_OK;
+  const int cn1 = std::max(n1, c->cap_n1), cs2 = std::max(s2, c->cap_s2);
+  free_ws(c);
+  const size_t R = (size_t)c->chunk_rays, l = (size_t)c->l;
+  size_t tot = 0;
+  auto A = [&](void** p, size_t bytes) -> int {
+    if (cudaMalloc(p, bytes) != cudaSuccess) { cudaGetLastError(); return STNERF_ENOMEM; }
+    tot += bytes;
+    return STNERF_OK;
+  };
+  int rc = 0;
+  rc |= A((void**)&c->t_coarse, l * R * cn1 * 4);
+  rc |= A((void**)&c->raw_coarse, l * R * cn1 * 16);
+  rc |= A((void**)&c->t_fine, l * R * cs2 * 4);
+  rc |= A((void**)&c->raw_fine, l * R * cs2 * 16);
+  rc |= A((void**)&c->xyz, R * cs2 * 12);
+  rc |= A((void**)&c->mask_ws, l * R);
+  rc |= A((void**)&c->hit, l * R * 4);
+  rc |= A((void**)&c->counts, STNERF_MAX_LAYERS * 4);
+  rc |= A((void**)&c->lerp_flags, STNERF_MAX_LAYERS * 4);
+  if (rc) { free_ws(c); return STNERF_ENOMEM; }
+  c->cap_n1 = cn1; c->cap_s2 = cs2; c->ws_bytes = tot;
+  return STNERF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing (host): state_dict order blob -> transposed [k][n] fp32 for the SIMT kernels
+// ---------------------------------------------------------------------------------------------------------
+static void transpose_into(std::vector<float>& dst, const float* W, int N, int K) {   // W (N,K) -> [K][N]
+  const size_t base = dst.size();
+  dst.resize(base + (size_t)N * K);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) dst[base + (size_t)k * N + n] = W[(size_t)n * K + k];
+}
+
+static int upload(float** dev, const std::vector<float>& host) {
+  if (*dev) { cudaFree(*dev); *dev = nullptr; }
+  STNERF_CUDA(cudaMalloc((void**)dev, host.size() * sizeof(float)));
+  STNERF_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return STNERF_OK;
+}
+
+extern "C" {
+
+const char* stnerf_strerror(int code) {
+  switch (code) {
+    case STNERF_OK: return "ok";
+    case STNERF_EINVAL: return "invalid argument";
+    case STNERF_ENODEVICE: return "no usable CUDA device (needs sm_100)";
+    case STNERF_ECUDA: return "CUDA runtime error (see stnerf_last_cuda_error)";
+    case STNERF_ENOWEIGHTS: return "network weights not loaded";
+    case STNERF_ENOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+const char* stnerf_last_cuda_error(void) { return g_cuda_err; }
+uint64_t stnerf_launch_count(void) { return g_launches; }
+
+int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
+  if (!out || !d || d->n_layers < 2 || d->n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STNERF_ENODEVICE; }
+  int dev = 0;
+  STNERF_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  STNERF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return STNERF_ENODEVICE;     // the cubin is sm_100a only
+  stnerf_ctx* c = new (std::nothrow) stnerf_ctx();
+  if (!c) return STNERF_ENOMEM;
+  c->desc = *d;
+  c->l = d->n_layers;
+  c->device = dev;
+  c->num_sms = prop.multiProcessorCount;
+  c->precision = d->precision;
+  c->chunk_rays = d->chunk_rays > 0 ? d->chunk_rays : 65536;
+  if (cudaMalloc((void**)&c->any_frac, 4) != cudaSuccess) { delete c; return STNERF_ENOMEM; }
+  *out = c;
+  return STNERF_OK;
+}
+
+void stnerf_destroy(stnerf_handle c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  free_ws(c);
+  for (int f = 0; f < 2; ++f)
+    for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->space[f][i].blob); tc_free(c->space[f][i].tc); }
+  for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->motion[i].blob); tc_free(c->motion[i].tc); }
+  cudaFree(c->h_rays); cudaFree(c->h_out); cudaFree(c->h_mask); cudaFree(c->any_frac);
+  if (c->prof_counts) cudaFreeHost(c->prof_counts);
+  delete c;
+}
+
+int stnerf_set_precision(stnerf_handle c, int precision) {
+  if (!c || precision < 0 || precision > 2) return STNERF_EINVAL;
+  c->precision = precision;
+  return STNERF_OK;
+}
+
+int stnerf_reserve(stnerf_handle c, int n1, int n2) {
+  if (!c || n1 < 3 || n1 > STNERF_MAX_N1 || n2 < 0 || n1 + n2 > STNERF_MAX_S) return STNERF_EINVAL;
+  return ensure_ws(c, n1, n1 + n2);
+}
+size_t stnerf_workspace_bytes(stnerf_handle c) { return c ? c->ws_bytes : 0; }
+
+int stnerf_load_spacenet(stnerf_handle c, int layer, int fine, const float* blob, size_t n) {
+  if (!c || !blob || layer < 0 || layer >= c->l || (fine != 0 && fine != 1)) return STNERF_EINVAL;
+  const bool use_time = (n == (size_t)SPACENET_FLOATS_TIME);
+  if (!use_time && n != (size_t)SPACENET_FLOATS_NOTIME) return STNERF_EINVAL;
+  if ((c->desc.space_time[layer] != 0) != use_time) return STNERF_EINVAL;
+  const int krgb = HID + PE_DIR + (use_time ? PE_TIME : 0);
+  // walk the blob in state_dict order
+  const float* p = blob;
+  std::vector<float> host;
+  size_t off_w[7], off_b[7];
+  const int Ks[7] = {PE_POS, HID, HID, HID, HID + PE_POS, HID, HID};
+  for (int i = 0; i < 7; ++i) {
+    off_w[i] = host.size();
+    transpose_into(host, p, HID, Ks[i]);
+    p += (size_t)HID * Ks[i];
+    off_b[i] = host.size();
+    host.insert(host.end(), p, p + HID);
+    p += HID;
+  }
+  const size_t off_ws = host.size();
+  host.insert(host.end(), p, p + HID); p += HID;
+  const float b_sigma = *p++;
+  const size_t off_wh = host.size();
+  transpose_into(host, p, HEAD, krgb); p += (size_t)HEAD * krgb;
+  const size_t off_bh = host.size();
+  host.insert(host.end(), p, p + HEAD); p += HEAD;
+  const size_t off_wo = host.size();
+  host.insert(host.end(), p, p + 3 * HEAD); p += 3 * HEAD;
+  const float b_o[3] = {p[0], p[1], p[2]};
+  SpaceNetDev& N = c->space[fine][layer];
+  int rc = upload(&N.blob, host);
+  if (rc) return rc;
+  for (int i = 0; i < 7; ++i) { N.w.w[i] = N.blob + off_w[i]; N.w.b[i] = N.blob + off_b[i]; }
+  N.w.w_sigma = N.blob + off_ws; N.w.b_sigma = b_sigma;
+  N.w.w_rgbh = N.blob + off_wh; N.w.b_rgbh = N.blob + off_bh;
+  N.w.w_rgbo = N.blob + off_wo;
+  for (int a = 0; a < 3; ++a) N.w.b_rgbo[a] = b_o[a];
+  N.w.use_time = use_time ? 1 : 0;
+  rc = tc_pack_spacenet(N.tc, blob, use_time);
+  if (rc) return rc;
+  N.loaded = true;
+  return STNERF_OK;
+}
+
+int stnerf_load_motionnet(stnerf_handle c, int layer, const float* blob, size_t n) {
+  if (!c || !blob || layer < 1 || layer >= c->l || n != (size_t)MOTIONNET_FLOATS) return STNERF_EINVAL;
+  const float* p = blob;
+  std::vector<float> host;
+  size_t off_w[5], off_b[5];
+  for (int i = 0; i < 5; ++i) {
+    const int K = i == 0 ? PE_MOTION : HEAD;
+    off_w[i] = host.size();
+    transpose_into(host, p, HEAD, K); p += (size_t)HEAD * K;
+    off_b[i] = host.size();
+    host.insert(host.end(), p, p + HEAD); p += HEAD;
+  }
+  const size_t off_wo = host.size();
+  host.insert(host.end(), p, p + 3 * HEAD); p += 3 * HEAD;
+  MotionNetDev& N = c->motion[layer];
+  int rc = upload(&N.blob, host);
+  if (rc) return rc;
+  for (int i = 0; i < 5; ++i) { N.w.w[i] = N.blob + off_w[i]; N.w.b[i] = N.blob + off_b[i]; }
+  N.w.w_out = N.blob + off_wo;
+  for (int a = 0; a < 3; ++a) N.w.b_out[a] = p[a];
+  rc = tc_pack_motionnet(N.tc, blob);
+  if (rc) return rc;
+  N.loaded = true;
+  return STNERF_OK;
+}
+
+int stnerf_set_scene(stnerf_handle c, const stnerf_scene* s) {
+  if (!c || !s) return STNERF_EINVAL;
+  c->scene = *s;
+  DevScene& d = c->dscene;
+  memset(&d, 0, sizeof(d));
+  for (int i = 0; i < c->l; ++i) {
+    for (int a = 0; a < 3; ++a) { d.bmin[i][a] = s->bmin[i][a]; d.bmax[i][a] = s->bmax[i][a]; }
+    d.shown[i] = s->shown[i];
+    if (s->scale_coarse_on[i] || s->scale_fine_on[i]) {
+      if (s->scale[i] == 0.0f) return STNERF_EINVAL;
+    }
+  }
+  d.near_plane = s->near_plane; d.alpha2 = s->alpha_layer2;
+  d.thr_layer = s->density_threshold; d.thr_bkgd = s->bkgd_density_threshold;
+  d.boarder = s->boarder_weight; d.apply_thr = s->apply_thresholds; d.n_layers = c->l;
+  c->have_scene = true;
+  return STNERF_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// one pass of the networks over a chunk
+// ---------------------------------------------------------------------------------------------------------
+static void fill_edit(PointSrc& s, const stnerf_scene& sc, int layer, bool fine) {
+  s.shift_on = sc.shift_on[layer];
+  s.scale_on = fine ? sc.scale_fine_on[layer] : sc.scale_coarse_on[layer];
+  for (int a = 0; a < 3; ++a) { s.shift[a] = sc.shift[layer][a]; s.pivot[a] = sc.pivot[a]; }
+  s.scale = sc.scale[layer];
+  if (!s.scale_on) s.scale = 1.0f;
+}
+
+static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, float* raw, float* rgb, float* sigma,
+                        cudaStream_t st, int count_slot = -1) {
+  if (!net.loaded) return STNERF_ENOWEIGHTS;
+  ProfScope ps(c, 0, (double)src.n_slots * src.S, count_slot, src.S, st);
+  if (c->precision == STNERF_PREC_FP32_SIMT)
+    return launch_spacenet_simt(src, net.w, raw, 0, rgb, sigma, c->num_sms, st);
+  return tc_launch_spacenet(src, net.tc, net.w, c->precision, raw, rgb, sigma, c->num_sms, st);
+}
+static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, const int* lerp_flag, int lerp_force,
+                         float* xyz_out, float* flow_out, cudaStream_t st, int count_slot = -1) {
+  if (!net.loaded) return STNERF_ENOWEIGHTS;
+  ProfScope ps(c, 1, (double)src.n_slots * src.S, count_slot, src.S, st);
+  if (c->precision == STNERF_PREC_FP32_SIMT)
+    return launch_motionnet_simt(src, net.w, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st);
+  return tc_launch_motionnet(src, net.tc, net.w, c->precision, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st);
+}
+
+static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_stride, bool fine, int S, cudaStream_t st,
+                    int chunk_slot) {
+  const long long R = c->chunk_rays;
+  const float* tbuf = fine ? c->t_fine : c->t_coarse;
+  float* rawbuf = fine ? c->raw_fine : c->raw_coarse;
+  const long long tl = R * (fine ? c->cap_s2 : c->cap_n1);      // layer strides of the workspace arrays
+  for (int i = 0; i < c->l; ++i) {
+    if (i > 0 && !c->scene.shown[i]) continue;                  // hidden performers: sigma = rgb = 0 (:401, :556)
+    PointSrc s;
+    memset(&s, 0, sizeof(s));
+    s.mode = SRC_MARCH;
+    s.rays = rays; s.ray_stride = ray_stride;
+    s.t = tbuf + i * tl;
+    s.S = S; s.layer = i;
+    s.pos_stride = 3; s.time_stride = 1;
+    fill_edit(s, c->scene, i, fine);
+    float* raw = rawbuf + (size_t)i * tl * 4;
+    int rc;
+    if (i == 0) {
+      s.hit = nullptr; s.count = nullptr; s.n_slots = n;
+      rc = run_spacenet(c, s, c->space[fine ? 1 : 0][0], raw, nullptr, nullptr, st);
+      if (rc) return rc;
+      continue;
+    }
+    s.hit = c->hit + (size_t)i * R;
+    s.count = c->counts + i;
+    rc = run_motionnet(c, s, c->motion[i], c->lerp_flags + i, -1, c->xyz, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
+    if (rc) return rc;
+    s.mode = SRC_XYZ;
+    s.pos = c->xyz;
+    rc = run_spacenet(c, s, c->space[fine ? 1 : 0][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
+    if (rc) return rc;
+  }
+  return STNERF_OK;
+}
+
+extern "C" {
+
+int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_stride, int n1, int n2, int only_coarse,
+                  const float* jitter, const float* u, uint64_t seed, float* out, uint8_t* ray_mask, void* stream) {
+  if (!c || !rays || !out || n_rays < 0) return STNERF_EINVAL;
+  if (!c->have_scene) return STNERF_EINVAL;
+  if (ray_stride < 6 + c->l) return STNERF_EINVAL;              // the reference prints + exit(-1) (:162-163)
+  if (n1 < 3 || n1 > STNERF_MAX_N1) return STNERF_EINVAL;
+  if (only_coarse) n2 = 0;
+  if (n2 < 0 || n1 + n2 > STNERF_MAX_S) return STNERF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_ws(c, n1, n1 + n2);
+  if (rc) return rc;
+  const int l = c->l, S2 = n1 + n2;
+  const long long R = c->chunk_rays, N = n_rays;
+  const long long plane = 5 * N;
+  for (long long c0 = 0; c0 < N; c0 += R) {
+    const long long n = std::min(R, N - c0);
+    const float* rch = rays + c0 * ray_stride;
+    STNERF_CUDA(cudaMemsetAsync(c->counts, 0, STNERF_MAX_LAYERS * 4, st));
+    STNERF_CUDA(cudaMemsetAsync(c->lerp_flags, 0, STNERF_MAX_LAYERS * 4, st));
+    uint8_t* mask = ray_mask ? ray_mask + c0 : c->mask_ws;
+    const long long mask_ls = ray_mask ? N : R;
+    int chunk_slot = -1;
+    {
+      ProfScope ps(c, 2, (double)n, -1, 1, st);
+      rc = launch_sample(rch, n, ray_stride, c->dscene, l, n1, jitter ? jitter + c0 * n1 : nullptr, N * n1, seed, c0,
+                         c->t_coarse, R * c->cap_n1, mask, mask_ls, c->hit, R, c->counts, c->lerp_flags, st);
+      if (rc) return rc;
+    }
+    if (c->prof_on && c->prof_counts && c->prof_chunks < PROF_MAX_CHUNKS) {
+      chunk_slot = c->prof_chunks++;
+      STNERF_CUDA(cudaMemcpyAsync(c->prof_counts + chunk_slot * 8, c->counts, 32, cudaMemcpyDeviceToHost, st));
+    }
+    // NOTE: the workspace t arrays are laid out with the *capacity* sample counts as layer stride but the
+    // per-ray stride is the live n1 / S2, so a ray's samples stay contiguous.
+    rc = run_nets(c, rch, n, ray_stride, false, n1, st, chunk_slot);
+    if (rc) return rc;
+    CompositeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.t = c->t_coarse; a.t_layer_stride = R * c->cap_n1;
+    a.raw = c->raw_coarse; a.raw_layer_stride = R * c->cap_n1 * 4;
+    a.mask = mask; a.mask_layer_stride = mask_ls;
+    a.u = u ? u + c0 * n2 : nullptr; a.u_layer_stride = N * n2;
+    a.t_fine = c->t_fine; a.tf_layer_stride = R * c->cap_s2;
+    a.out = out; a.n_total = N; a.ray_base = c0; a.n = n;
+    a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed;
+    {
+      ProfScope ps(c, 3, (double)n, -1, 1, st);
+      rc = launch_composite_pass(a, c->dscene, l, st);
+      if (rc) return rc;
+    }
+    if (n2 > 0) {
+      rc = run_nets(c, rch, n, ray_stride, true, S2, st, chunk_slot);
+      if (rc) return rc;
+      a.t = c->t_fine; a.t_layer_stride = R * c->cap_s2;
+      a.raw = c->raw_fine; a.raw_layer_stride = R * c->cap_s2 * 4;
+      a.u = nullptr; a.t_fine = nullptr;
+      a.out = out + (size_t)(l + 1) * plane;
+      a.S = S2; a.n2 = 0; a.fine = 1;
+      ProfScope ps(c, 3, (double)n, -1, 1, st);
+      rc = launch_composite_pass(a, c->dscene, l, st);
+      if (rc) return rc;
+    }
+  }
+  return STNERF_OK;
+}
+
+static int grow(void** p, size_t* have, size_t want) {
+  if (want <= *have) return STNERF_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  if (cudaMalloc(p, want) != cudaSuccess) { cudaGetLastError(); return STNERF_ENOMEM; }
+  *have = want;
+  return STNERF_OK;
+}
+
+int stnerf_render_host(stnerf_handle c, const float* rays_host, int64_t n_rays, int ray_stride, int n1, int n2,
+                       int only_coarse, uint64_t seed, float* out_host, uint8_t* ray_mask_host, void* stream) {
+  if (!c || !rays_host || !out_host || n_rays <= 0) return STNERF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rb = (size_t)n_rays * ray_stride * 4, ob = (size_t)2 * (c->l + 1) * 5 * n_rays * 4,
+               mb = (size_t)c->l * n_rays;
+  int rc = grow((void**)&c->h_rays, &c->h_rays_bytes, rb);
+  rc |= grow((void**)&c->h_out, &c->h_out_bytes, ob);
+  rc |= grow((void**)&c->h_mask, &c->h_mask_bytes, mb);
+  if (rc) return STNERF_ENOMEM;
+  STNERF_CUDA(cudaMemcpyAsync(c->h_rays, rays_host, rb, cudaMemcpyHostToDevice, st));
+  rc = stnerf_render(c, c->h_rays, n_rays, ray_stride, n1, n2, only_coarse, nullptr, nullptr, seed, c->h_out, c->h_mask, st);
+  if (rc) return rc;
+  const size_t ob_used = only_coarse ? ob / 2 : ob;
+  STNERF_CUDA(cudaMemcpyAsync(out_host, c->h_out, ob_used, cudaMemcpyDeviceToHost, st));
+  if (ray_mask_host) STNERF_CUDA(cudaMemcpyAsync(ray_mask_host, c->h_mask, mb, cudaMemcpyDeviceToHost, st));
+  STNERF_CUDA(cudaStreamSynchronize(st));
+  return STNERF_OK;
+}
+
+int stnerf_profile_begin(stnerf_handle c) {
+  if (!c) return STNERF_EINVAL;
+  if (!c->prof_counts) STNERF_CUDA(cudaHostAlloc((void**)&c->prof_counts, (size_t)PROF_MAX_CHUNKS * 32, cudaHostAllocDefault));
+  for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c->prof.clear();
+  c->prof_chunks = 0;
+  c->prof_on = true;
+  return STNERF_OK;
+}
+
+int stnerf_profile_end(stnerf_handle c, stnerf_profile* out) {
+  if (!c || !out) return STNERF_EINVAL;
+  c->prof_on = false;
+  STNERF_CUDA(cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) out->ms[r.cls] += ms;
+    out->launches[r.cls] += 1;
+    out->points[r.cls] += r.count_slot >= 0 ? (double)c->prof_counts[r.count_slot] * r.S : r.points;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  c->prof.clear();
+  return STNERF_OK;
+}
+
+int stnerf_raygen(const float* Kinv_host, const float* T_host, int H, int W, int row0, int row_step, int n_rows,
+                  const float* frame_ids_host, int n_frame_ids, float* rays, int ray_stride, void* stream) {
+  if (!Kinv_host || !T_host || !rays || row_step < 1 || row0 < 0 || (n_frame_ids > 0 && !frame_ids_host))
+    return STNERF_EINVAL;
+  return launch_raygen(Kinv_host, T_host, H, W, row0, row_step, n_rows, frame_ids_host, n_frame_ids, rays, ray_stride,
+                       (cudaStream_t)stream);
+}
+
+int stnerf_intersect_sample(const float* rays, int64_t n, int ray_stride, const float* bmin_host, const float* bmax_host,
+                            int is_bkgd, int n1, const float* jitter, float* t, float* xyz, uint8_t* mask,
+                            float* tfar_tnear, void* stream) {
+  if (!rays || !bmin_host || !bmax_host || !jitter || n1 < 1 || ray_stride < 6) return STNERF_EINVAL;
+  return launch_intersect_sample(rays, n, ray_stride, bmin_host, bmax_host, is_bkgd, n1, jitter, t, xyz, mask,
+                                 tfar_tnear, (cudaStream_t)stream);
+}
+
+int stnerf_composite(const float* t, const float* rgb, const float* sigma, int64_t n, int S, float boarder, float* color,
+                     float* depth, float* acc, float* w, void* stream) {
+  if (!t || !rgb || !sigma || !color || !depth || !acc || S < 1) return STNERF_EINVAL;
+  return launch_composite_simple(t, rgb, sigma, n, S, boarder, color, depth, acc, w, (cudaStream_t)stream);
+}
+
+int stnerf_sample_pdf(const float* t, const float* w, const float* u, int64_t n, int n1, int n2, float* z, float* t_fine,
+                      void* stream) {
+  if (!t || !w || !u || (!z && !t_fine) || n1 > STNERF_MAX_N1 * 4 || n1 + n2 > 4096) return STNERF_EINVAL;
+  return launch_sample_pdf(t, w, u, n, n1, n2, z, t_fine, (cudaStream_t)stream);
+}
+
+int stnerf_positional_encoding(const float* x, int64_t P, int dim, int n_freq, float* out, void* stream) {
+  if (!x || !out || dim < 1 || n_freq < 0 || n_freq > 16) return STNERF_EINVAL;
+  return launch_posenc(x, P, dim, n_freq, out, (cudaStream_t)stream);
+}
+
+int stnerf_spacenet(stnerf_handle c, int layer, int fine, const float* pos, const float* dirs, const float* times,
+                    int64_t P, float* rgb, float* sigma, void* stream) {
+  if (!c || !pos || !dirs || !rgb || !sigma || layer < 0 || layer >= c->l || (fine != 0 && fine != 1)) return STNERF_EINVAL;
+  SpaceNetDev& net = c->space[fine][layer];
+  if (!net.loaded) return STNERF_ENOWEIGHTS;
+  if (net.w.use_time && !times) return STNERF_EINVAL;
+  PointSrc s;
+  memset(&s, 0, sizeof(s));
+  s.mode = SRC_EXPLICIT; s.pos = pos; s.dirs = dirs; s.times = times; s.pos_stride = 3; s.time_stride = 1;
+  s.n_slots = P; s.S = 1; s.scale = 1.f;
+  return run_spacenet(c, s, net, nullptr, rgb, sigma, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+__global__ void any_fraction_kernel(const float* __restrict__ xyzt, long long P, int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    const float t = xyzt[4 * i + 3];
+    if (floorf(t) != t) atomicOr(flag, 1);
+  }
+}
+
+extern "C" int stnerf_motionnet(stnerf_handle c, int layer, const float* xyzt, int64_t P, int lerp_mode, float* flow,
+                                void* stream) {
+  if (!c || !xyzt || !flow || layer < 1 || layer >= c->l || lerp_mode < -1 || lerp_mode > 1) return STNERF_EINVAL;
+  MotionNetDev& net = c->motion[layer];
+  if (!net.loaded) return STNERF_ENOWEIGHTS;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lerp_mode < 0 && P > 0) {
+    STNERF_CUDA(cudaMemsetAsync(c->any_frac, 0, 4, st));
+    any_fraction_kernel<<<(int)((P + 255) / 256), 256, 0, st>>>(xyzt, P, c->any_frac);
+    STNERF_LAUNCH_CHECK();
+  }
+  PointSrc s;
+  memset(&s, 0, sizeof(s));
+  s.mode = SRC_EXPLICIT; s.pos = xyzt; s.times = xyzt + 3; s.pos_stride = 4; s.time_stride = 4;
+  s.n_slots = P; s.S = 1; s.scale = 1.f;
+  return run_motionnet(c, s, net, c->any_frac, lerp_mode, nullptr, flow, st);
+}

@@ -1,0 +1,409 @@
+// Alpha compositing, inverse-CDF resampling and the depth-ordered merge of all layers (warp-per-ray kernels).
+//
+// Restates layers/render_layer.py:8-58 (gen_weight / VolumeRenderer), utils/sample_pdf.py:18-63 and the
+// sort-merge of modeling/layered_rfrender.py:425-448 (coarse) / :587-606 (fine).  fp32, compiled with
+// -fmad=false so every product/sum rounds like the separate ATen ops of the reference.  Scans use warp
+// shuffles (tree order), so results agree with torch.cumprod / cumsum to a few ulp, not bit for bit.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace stnerf {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+__device__ __forceinline__ float warp_incl_mul(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float n = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v = v * n;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_incl_add(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float n = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v = v + n;
+  }
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// order-preserving map float -> uint32 (total order incl. negatives)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// In-shared-memory bitonic sort of P (power of two) elements by one warp.
+template <typename T>
+__device__ __forceinline__ void warp_bitonic_sort(T* a, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int p = i ^ j;
+        if (p > i) {
+          const T x = a[i], y = a[p];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[p] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// gen_weight + VolumeRenderer.forward over `count` samples addressed through `at(j)` (position in the
+// per-warp arrays).  All lanes return the reduced color/depth/acc.  If w_out != null, w_out[j] = weight.
+template <typename At>
+__device__ __forceinline__ void composite_run(int count, At at, const float* s_t, const float* s_sig, const float* s_r,
+                                              const float* s_g, const float* s_b, float boarder, float near_cut,
+                                              bool use_near_cut, float* w_out, int lane, float out[5]) {
+  float carry = 1.0f;                      // cumprod of [1, 1-alpha+1e-10, ...][:-1]  (render_layer.py:15)
+  float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+  for (int base = 0; base < count; base += 32) {
+    const int j = base + lane;
+    const bool valid = j < count;
+    float f = 1.0f, alpha = 0.0f, tj = 0.0f;
+    int pj = 0;
+    if (valid) {
+      pj = at(j);
+      tj = s_t[pj];
+      const float delta = (j == count - 1) ? boarder : (s_t[at(j + 1)] - tj);     // render_layer.py:37-40
+      float sg = s_sig[pj];
+      if (use_near_cut && tj < near_cut) sg = 0.0f;                                // layered_rfrender.py:605
+      const float e = expf(-fmaxf(sg, 0.0f) * delta);                              // render_layer.py:11
+      alpha = 1.0f - e;
+      f = (1.0f - alpha) + 1e-10f;                                                 // render_layer.py:12
+    }
+    const float incl = warp_incl_mul(f, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    carry = carry * __shfl_sync(FULL, incl, 31);
+    if (valid) {
+      const float w = alpha * T;
+      if (w_out) w_out[j] = w;
+      cr += s_r[pj] * w;                                                           // render_layer.py:45
+      cg += s_g[pj] * w;
+      cb += s_b[pj] * w;
+      cd += w * tj;                                                                // :46
+      ca += w;                                                                     // :47
+    }
+  }
+  out[0] = warp_sum(cr); out[1] = warp_sum(cg); out[2] = warp_sum(cb);
+  out[3] = warp_sum(cd); out[4] = warp_sum(ca);
+}
+
+// utils/sample_pdf.py:18-63 for one ray: t[n1] (any order), w[n1] full weights, n2 uniforms -> z written to
+// zbuf[0..n2).  cdf is an (n1-1)-float scratch.
+template <typename U>
+__device__ __forceinline__ void sample_pdf_ray(const float* s_t, const float* s_w, int n1, int n2, U get_u,
+                                               float* cdf, float* zbuf, int lane) {
+  const int nb = n1 - 2;                      // weights[..., 1:-1]
+  float part = 0.f;
+  for (int m = lane; m < nb; m += 32) part += s_w[m + 1] + 1e-5f;                  // :21
+  const float tot = warp_sum(part);
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.0f;                                                    // :24
+  for (int base = 0; base < nb; base += 32) {
+    const int m = base + lane;
+    const float pdf = (m < nb) ? (s_w[m + 1] + 1e-5f) / tot : 0.0f;                // :22
+    const float incl = warp_incl_add(pdf, lane);
+    if (m < nb) cdf[m + 1] = carry + incl;                                         // :23
+    carry = carry + __shfl_sync(FULL, incl, 31);
+  }
+  __syncwarp();
+  const int nc = n1 - 1;                      // len(cdf) == len(bins)
+  for (int j = lane; j < n2; j += 32) {
+    const float uu = get_u(j);
+    int lo = 0, hi = nc;                      // searchsorted(right=True): first index with cdf > u (:47)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0);                                              // :48
+    const int above = min(lo, nc - 1);                                             // :49
+    const float cb = cdf[below], ca = cdf[above];
+    const float bb = 0.5f * (s_t[below + 1] + s_t[below]);                         // :20
+    const float ba = 0.5f * (s_t[above + 1] + s_t[above]);
+    float den = ca - cb;
+    if (den < 1e-5f) den = 1.0f;                                                   // :59
+    const float tt = (uu - cb) / den;
+    zbuf[j] = bb + tt * (ba - bb);                                                 // :61
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5 / K6: one pass (coarse or fine) of per-layer + merged compositing for a chunk of rays.
+// ---------------------------------------------------------------------------------------------------------
+struct PassSmem {
+  int per_warp_floats, off_sig, off_r, off_g, off_b, off_w, off_cdf, off_sort, sort_floats;
+};
+
+__host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static PassSmem pass_layout(int l, int S, int n2) {
+  PassSmem L;
+  const int tot = l * S;
+  L.off_sig = tot; L.off_r = 2 * tot; L.off_g = 3 * tot; L.off_b = 4 * tot;
+  L.off_w = 5 * tot;
+  L.off_cdf = L.off_w + S;
+  L.off_sort = L.off_cdf + S;
+  L.off_sort = (L.off_sort + 1) & ~1;       // 8-byte aligned for the uint64 keys
+  int sf = 2 * next_pow2(tot);
+  if (n2 > 0 && next_pow2(S + n2) > sf) sf = next_pow2(S + n2);
+  L.sort_floats = sf;
+  L.per_warp_floats = (L.off_sort + sf + 3) & ~3;
+  return L;
+}
+
+__global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scene, int n_layers, const PassSmem L) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* base = smem + (size_t)warp * L.per_warp_floats;
+  float* s_t = base;
+  float* s_sig = base + L.off_sig;
+  float* s_r = base + L.off_r;
+  float* s_g = base + L.off_g;
+  float* s_b = base + L.off_b;
+  float* s_w = base + L.off_w;
+  float* s_cdf = base + L.off_cdf;
+  float* s_sortf = base + L.off_sort;
+  unsigned long long* s_sort64 = reinterpret_cast<unsigned long long*>(s_sortf);
+
+  const int S = a.S, n2 = a.n2;
+  const bool fine = a.fine != 0;
+  const float near_p = scene.near_plane, boarder = scene.boarder;
+  const bool thr_on = scene.apply_thr != 0;
+  const long long plane = 5 * a.n_total;
+
+  for (long long r = (long long)blockIdx.x * wpb + warp; r < a.n; r += (long long)gridDim.x * wpb) {
+    const long long rg = a.ray_base + r;
+    int n_m = 0;                                  // entries gathered for the merged composite
+    for (int i = 0; i < n_layers; ++i) {
+      float* oimg = a.out + (size_t)(1 + i) * plane;
+      const bool hit = (i == 0) || (a.mask[i * a.mask_layer_stride + r] != 0);
+      if (!hit) {                                 // all samples at t=-1000 with sigma 0: inert
+        if (lane < 3) oimg[rg * 3 + lane] = 0.0f;
+        if (lane == 3) oimg[3 * a.n_total + rg] = 0.0f;
+        if (lane == 4) oimg[4 * a.n_total + rg] = 0.0f;
+        continue;
+      }
+      const bool shown = (i == 0) || (scene.shown[i] != 0);
+      const int off = n_m;
+      const float* tp = a.t + i * a.t_layer_stride + r * S;
+      const float4* rp = reinterpret_cast<const float4*>(a.raw + i * a.raw_layer_stride) + r * S;
+      for (int k = lane; k < S; k += 32) {
+        const float tk = tp[k];
+        float sg = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (shown) {
+          const float4 v = rp[k];
+          sg = v.w; cr = v.x; cg = v.y; cb = v.z;
+          if (!fine) {
+            if (i > 0) {
+              if (tk < 0.0f) sg = 0.0f;                                         // layered_rfrender.py:414
+              if (thr_on && sg < scene.thr_layer) sg = 0.0f;                   // :416-418
+            } else if (tk < near_p) {
+              sg = 0.0f;                                                        // :422
+            }
+          } else {
+            if (i == 0) {
+              if (thr_on && sg < scene.thr_bkgd) sg = 0.0f;                    // :538-547
+            } else {
+              if (thr_on && sg < scene.thr_layer) sg = 0.0f;                   // :564-566
+              if (i == 2) sg = sg * scene.alpha2;                              // :575-576
+            }
+          }
+        }
+        s_t[off + k] = tk;
+        s_sig[off + k] = sg;
+        s_r[off + k] = sigmoidf_ref(cr);
+        s_g[off + k] = sigmoidf_ref(cg);
+        s_b[off + k] = sigmoidf_ref(cb);
+      }
+      __syncwarp();
+      float o5[5];
+      const bool want_w = (!fine) && n2 > 0;
+      composite_run(S, [off](int j) { return off + j; }, s_t, s_sig, s_r, s_g, s_b, boarder, 0.f, false,
+                    want_w ? s_w : nullptr, lane, o5);
+      if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
+      if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
+      if (lane == 4) oimg[4 * a.n_total + rg] = o5[4];
+      __syncwarp();
+      if (want_w) {
+        // hierarchical resampling of this layer (layered_rfrender.py:459-463)
+        const float* up = a.u ? a.u + i * a.u_layer_stride + r * n2 : nullptr;
+        const uint64_t seed = a.seed;
+        sample_pdf_ray(s_t + off, s_w, S, n2,
+                       [up, seed, i, rg](int j) {
+                         return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, (uint64_t)rg, (uint32_t)j);
+                       },
+                       s_cdf, s_sortf + S, lane);
+        const int S2 = S + n2, P = next_pow2(S2);
+        for (int k = lane; k < S; k += 32) s_sortf[k] = s_t[off + k];
+        for (int k = S2 + lane; k < P; k += 32) s_sortf[k] = CUDART_INF_F;
+        __syncwarp();
+        warp_bitonic_sort(s_sortf, P, lane);                                    // torch.sort(cat(t, z)) :462
+        float* tf = a.t_fine + i * a.tf_layer_stride + r * S2;
+        for (int k = lane; k < S2; k += 32) tf[k] = s_sortf[k];
+        __syncwarp();
+      }
+      n_m += S;
+    }
+    // ---- merged composite over every hit layer's samples, ordered by (t, cat index)  (:425-448 / :587-606)
+    {
+      const int P = next_pow2(n_m);
+      for (int j = lane; j < P; j += 32)
+        s_sort64[j] = (j < n_m) ? (((unsigned long long)float_key(s_t[j]) << 32) | (unsigned)j) : ~0ull;
+      __syncwarp();
+      warp_bitonic_sort(s_sort64, P, lane);
+      float o5[5];
+      composite_run(n_m, [s_sort64](int j) { return (int)(s_sort64[j] & 0xffffffffu); }, s_t, s_sig, s_r, s_g, s_b,
+                    boarder, near_p, fine, nullptr, lane, o5);
+      float* oimg = a.out;
+      if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
+      if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
+      if (lane == 4) oimg[4 * a.n_total + rg] = o5[4];
+      __syncwarp();
+    }
+  }
+}
+
+int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_layers, cudaStream_t st) {
+  if (a.n <= 0) return STNERF_OK;
+  const PassSmem L = pass_layout(n_layers, a.S, a.fine ? 0 : a.n2);
+  const size_t per_warp = (size_t)L.per_warp_floats * sizeof(float);
+  int wpb = (int)((200 * 1024) / per_warp);
+  if (wpb < 1) return STNERF_EINVAL;
+  if (wpb > 8) wpb = 8;
+  const size_t smem = per_warp * wpb;
+  static size_t configured = 0;
+  if (smem > configured) {
+    STNERF_CUDA(cudaFuncSetAttribute(composite_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  long long blocks = (a.n + wpb - 1) / wpb;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  composite_pass_kernel<<<(int)blocks, wpb * 32, smem, st>>>(a, scene, n_layers, L);
+  STNERF_LAUNCH_CHECK();
+  return STNERF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Unit entry point a10: VolumeRenderer.forward on explicit (t, rgb, sigma) arrays.  Warp per ray, streaming:
+// 20 B/sample in, 4 B/sample out (weights) -- the HBM-roofline kernel of the compositing stage.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void composite_simple_kernel(const float* __restrict__ t, const float* __restrict__ rgb,
+                                        const float* __restrict__ sigma, long long n, int S, float boarder,
+                                        float* __restrict__ color, float* __restrict__ depth, float* __restrict__ acc,
+                                        float* __restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = wid; r < n; r += nw) {
+    const float* tp = t + r * S;
+    const float* sp = sigma + r * S;
+    const float* cp = rgb + r * S * 3;
+    float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+    for (int base = 0; base < S; base += 32) {
+      const int j = base + lane;
+      const bool valid = j < S;
+      float f = 1.0f, alpha = 0.0f;
+      const float tj = valid ? tp[j] : 0.0f;
+      float tn = __shfl_down_sync(FULL, tj, 1);
+      if (lane == 31) tn = (j + 1 < S) ? tp[j + 1] : 0.0f;
+      if (valid) {
+        const float delta = (j == S - 1) ? boarder : (tn - tj);
+        const float e = expf(-fmaxf(sp[j], 0.0f) * delta);
+        alpha = 1.0f - e;
+        f = (1.0f - alpha) + 1e-10f;
+      }
+      const float incl = warp_incl_mul(f, lane);
+      float excl = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      carry = carry * __shfl_sync(FULL, incl, 31);
+      if (valid) {
+        const float ww = alpha * T;
+        if (w) w[r * S + j] = ww;
+        cr += sigmoidf_ref(cp[3 * j]) * ww;
+        cg += sigmoidf_ref(cp[3 * j + 1]) * ww;
+        cb += sigmoidf_ref(cp[3 * j + 2]) * ww;
+        cd += ww * tj;
+        ca += ww;
+      }
+    }
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); cd = warp_sum(cd); ca = warp_sum(ca);
+    if (lane == 0) {
+      color[3 * r] = cr; color[3 * r + 1] = cg; color[3 * r + 2] = cb;
+      depth[r] = cd;
+      acc[r] = ca;
+    }
+  }
+}
+
+int launch_composite_simple(const float* t, const float* rgb, const float* sigma, long long n, int S, float boarder,
+                            float* color, float* depth, float* acc, float* w, cudaStream_t st) {
+  if (n <= 0) return STNERF_OK;
+  const int block = 256;
+  long long blocks = (n * 32 + block - 1) / block;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  composite_simple_kernel<<<(int)blocks, block, 0, st>>>(t, rgb, sigma, n, S, boarder, color, depth, acc, w);
+  STNERF_LAUNCH_CHECK();
+  return STNERF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Unit entry point a11: sample_pdf (+ optional sort-merge with the coarse depths).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sample_pdf_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ u,
+                                  long long n, int n1, int n2, float* __restrict__ z, float* __restrict__ t_fine,
+                                  int per_warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* s_t = smem + (size_t)warp * per_warp_floats;
+  float* s_w = s_t + n1;
+  float* s_cdf = s_w + n1;
+  float* s_sort = s_cdf + n1;
+  const int S2 = n1 + n2, P = next_pow2(S2);
+  for (long long r = (long long)blockIdx.x * wpb + warp; r < n; r += (long long)gridDim.x * wpb) {
+    for (int k = lane; k < n1; k += 32) { s_t[k] = t[r * n1 + k]; s_w[k] = w[r * n1 + k]; }
+    __syncwarp();
+    const float* up = u + r * n2;
+    sample_pdf_ray(s_t, s_w, n1, n2, [up](int j) { return up[j]; }, s_cdf, s_sort + n1, lane);
+    if (z) for (int j = lane; j < n2; j += 32) z[r * n2 + j] = s_sort[n1 + j];
+    if (t_fine) {
+      for (int k = lane; k < n1; k += 32) s_sort[k] = s_t[k];
+      for (int k = S2 + lane; k < P; k += 32) s_sort[k] = CUDART_INF_F;
+      __syncwarp();
+      warp_bitonic_sort(s_sort, P, lane);
+      for (int k = lane; k < S2; k += 32) t_fine[r * S2 + k] = s_sort[k];
+    }
+    __syncwarp();
+  }
+}
+
+int launch_sample_pdf(const float* t, const float* w, const float* u, long long n, int n1, int n2, float* z,
+                      float* t_fine, cudaStream_t st) {
+  if (n <= 0) return STNERF_OK;
+  if (n1 < 3 || n2 < 1) return STNERF_EINVAL;
+  const int per_warp = ((3 * n1 + next_pow2(n1 + n2)) + 3) & ~3;
+  const int wpb = 4;
+  const size_t smem = (size_t)per_warp * wpb * sizeof(float);
+  if (smem > 48 * 1024)
+    STNERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (n + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sample_pdf_kernel<<<(int)blocks, wpb * 32, smem, st>>>(t, w, u, n, n1, n2, z, t_fine, per_warp);
+  STNERF_LAUNCH_CHECK();
+  return STNERF_OK;
+}
+
+}  // namespace stnerf

@@ -1,0 +1,25 @@
+// tcgen05 (5th-gen tensor core) evaluation of SpaceNet / MotionNet: precision modes TC_3XF16 and TC_F16.
+#pragma once
+#include "common.cuh"
+
+namespace stnerf {
+
+// Weights of one network packed for the tensor-core kernels (see mlp_tc.cu for the layout).
+struct TcNet {
+  void* blob = nullptr;        // device: fp16 hi/lo weight blocks in the 128B-swizzled K-major SMEM image
+  size_t blob_bytes = 0;
+  float* aux = nullptr;        // device: fp32 biases / head weights
+  int n_blocks = 0;
+  int use_time = 0;
+};
+
+int tc_pack_spacenet(TcNet& net, const float* blob_host, bool use_time);
+int tc_pack_motionnet(TcNet& net, const float* blob_host);
+void tc_free(TcNet& net);
+int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* raw,
+                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st);
+int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW& w32, int precision,
+                        const int* lerp_flag_dev, int lerp_force, float* xyz_out, float* flow_out, int num_sms,
+                        cudaStream_t st);
+
+}  // namespace stnerf

@@ -1,0 +1,160 @@
+"""Thin object wrapper over the C ABI: owns a context handle, loads weights, sets the scene, renders.
+
+torch is used only for device memory and the current stream; every arithmetic step happens in libstnerf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+SPACENET_KEYS = ["stage1.0", "stage1.2", "stage1.4", "stage1.6", "stage2.0", "stage2.2", "stage2.4",
+                 "density_net.0", "rgb_net.1", "rgb_net.3"]
+MOTIONNET_KEYS = ["motion_net.%d" % i for i in (0, 2, 4, 6, 8, 10)]
+
+
+def _blob(sd: Dict[str, torch.Tensor], prefix: str, names: Sequence[str]) -> torch.Tensor:
+    parts = []
+    for n in names:
+        parts.append(sd[prefix + n + ".weight"].detach().to("cpu", torch.float32).reshape(-1))
+        parts.append(sd[prefix + n + ".bias"].detach().to("cpu", torch.float32).reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
+class NativeRenderer:
+    """One libstnerf context (one GPU, one set of networks)."""
+
+    def __init__(self, n_layers: int, space_time: Sequence[bool], precision: str = "fp32", chunk_rays: int = 0):
+        if not torch.cuda.is_available():
+            raise L.StnerfError("stnerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.l = int(n_layers)
+        desc = L.ModelDesc()
+        desc.n_layers = self.l
+        for i in range(self.l):
+            desc.space_time[i] = 1 if space_time[i] else 0
+        desc.precision = L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        desc.chunk_rays = int(chunk_rays)
+        self._h = C.c_void_p()
+        L.check(L.lib().stnerf_create(C.byref(self._h), C.byref(desc)), "stnerf_create")
+        self._scene = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().stnerf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Upload a reference-format state_dict (SURVEY App. B key names)."""
+        lib = L.lib()
+        for fine, pre in ((0, "bkgd_spacenet."), (1, "bkgd_spacenet_fine.")):
+            b = _blob(sd, pre, SPACENET_KEYS)
+            L.check(lib.stnerf_load_spacenet(self._h, 0, fine, L.ptr(b), b.numel()), "load bkgd spacenet")
+        for i in range(1, self.l):
+            for fine, grp in ((0, "spacenets"), (1, "spacenets_fine")):
+                b = _blob(sd, "%s.%d." % (grp, i - 1), SPACENET_KEYS)
+                L.check(lib.stnerf_load_spacenet(self._h, i, fine, L.ptr(b), b.numel()), "load spacenet %d" % i)
+            b = _blob(sd, "time_deform_nets.%d." % (i - 1), MOTIONNET_KEYS)
+            L.check(lib.stnerf_load_motionnet(self._h, i, L.ptr(b), b.numel()), "load motionnet %d" % i)
+
+    def set_precision(self, precision):
+        p = L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        L.check(L.lib().stnerf_set_precision(self._h, p), "stnerf_set_precision")
+
+    # ---- scene -----------------------------------------------------------------------------------------
+    def set_scene(self, scene: L.Scene):
+        self._scene = scene
+        L.check(L.lib().stnerf_set_scene(self._h, C.byref(scene)), "stnerf_set_scene")
+
+    # ---- render ----------------------------------------------------------------------------------------
+    def render(self, rays: torch.Tensor, n1: int, n2: int, only_coarse: bool = False,
+               jitter: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, seed: int = 0,
+               out: Optional[torch.Tensor] = None, ray_mask: Optional[torch.Tensor] = None):
+        """rays (N, >=6+l) fp32 CUDA.  Returns out (2, l+1, 5N) fp32 and ray_mask (l, N) uint8."""
+        assert rays.is_cuda and rays.dtype == torch.float32 and rays.dim() == 2
+        rays = rays if rays.is_contiguous() else rays.contiguous()
+        N = rays.shape[0]
+        if out is None:
+            out = torch.empty((2, self.l + 1, 5 * N), dtype=torch.float32, device=rays.device)
+        if ray_mask is None:
+            ray_mask = torch.empty((self.l, N), dtype=torch.uint8, device=rays.device)
+        for t, shape in ((jitter, (self.l, N, n1)), (u, (self.l, N, n2))):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, \
+                    (tuple(t.shape), shape)
+        with torch.cuda.device(rays.device):
+            L.check(L.lib().stnerf_render(self._h, L.ptr(rays), N, rays.stride(0), int(n1), int(n2),
+                                          1 if only_coarse else 0, L.ptr(jitter), L.ptr(None if only_coarse else u),
+                                          int(seed) & (2 ** 64 - 1), L.ptr(out), L.ptr(ray_mask), L.stream_ptr()),
+                    "stnerf_render")
+        return out, ray_mask
+
+    def render_host(self, rays_host: torch.Tensor, n1: int, n2: int, only_coarse: bool = False, seed: int = 0,
+                    out_host: Optional[torch.Tensor] = None, mask_host: Optional[torch.Tensor] = None):
+        """Host-buffer entry (H2D + render + D2H inside the call): the end-to-end path."""
+        assert not rays_host.is_cuda and rays_host.dtype == torch.float32 and rays_host.is_contiguous()
+        N = rays_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty((2, self.l + 1, 5 * N), dtype=torch.float32).pin_memory()
+        if mask_host is None:
+            mask_host = torch.empty((self.l, N), dtype=torch.uint8).pin_memory()
+        L.check(L.lib().stnerf_render_host(self._h, L.ptr(rays_host), N, rays_host.stride(0), int(n1), int(n2),
+                                           1 if only_coarse else 0, int(seed) & (2 ** 64 - 1), L.ptr(out_host),
+                                           L.ptr(mask_host), L.stream_ptr()), "stnerf_render_host")
+        return out_host, mask_host
+
+    # ---- per-stage entry points that need the networks ------------------------------------------------------
+    def spacenet(self, layer: int, fine: bool, pos, dirs, times=None):
+        P = pos.shape[0]
+        rgb = torch.empty((P, 3), dtype=torch.float32, device=pos.device)
+        sig = torch.empty((P, 1), dtype=torch.float32, device=pos.device)
+        L.check(L.lib().stnerf_spacenet(self._h, layer, 1 if fine else 0, L.ptr(pos.contiguous()),
+                                        L.ptr(dirs.contiguous()), L.ptr(None if times is None else times.contiguous()),
+                                        P, L.ptr(rgb), L.ptr(sig), L.stream_ptr()), "stnerf_spacenet")
+        return rgb, sig
+
+    def motionnet(self, layer: int, xyzt, lerp_mode: int = -1):
+        P = xyzt.shape[0]
+        flow = torch.empty((P, 3), dtype=torch.float32, device=xyzt.device)
+        L.check(L.lib().stnerf_motionnet(self._h, layer, L.ptr(xyzt.contiguous()), P, lerp_mode, L.ptr(flow),
+                                         L.stream_ptr()), "stnerf_motionnet")
+        return flow
+
+    def profile_begin(self):
+        L.check(L.lib().stnerf_profile_begin(self._h), "stnerf_profile_begin")
+
+    def profile_end(self) -> dict:
+        """Per kernel class device time (CUDA events on the launching stream): SpaceNet, MotionNet, sampling, compositing."""
+        p = L.Profile()
+        L.check(L.lib().stnerf_profile_end(self._h, C.byref(p)), "stnerf_profile_end")
+        names = ("spacenet", "motionnet", "sample", "composite")
+        return {n: {"ms": p.ms[i], "points": p.points[i], "launches": int(p.launches[i])} for i, n in enumerate(names)}
+
+    def workspace_bytes(self) -> int:
+        return int(L.lib().stnerf_workspace_bytes(self._h))
+
+
+def split_planes(out: torch.Tensor, l: int):
+    """(2, l+1, 5N) planes -> (fine_mixed, coarse_mixed, fine_layer, coarse_layer) tuples of (rgb, depth, acc)."""
+    N = out.shape[2] // 5
+
+    def trip(p):
+        return (p[:3 * N].view(N, 3), p[3 * N:4 * N].view(N, 1), p[4 * N:].view(N, 1))
+
+    coarse_mixed, fine_mixed = trip(out[0, 0]), trip(out[1, 0])
+    coarse_layer = [trip(out[0, 1 + i]) for i in range(l)]
+    fine_layer = [trip(out[1, 1 + i]) for i in range(l)]
+    return fine_mixed, coarse_mixed, fine_layer, coarse_layer
+
+
+def launch_count() -> int:
+    return int(L.lib().stnerf_launch_count())

@@ -1,0 +1,81 @@
+"""Helpers shared by the gpu tests, smoke() and bench.py: build the facade model for a golden case and run it."""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import cases as C  # noqa: E402
+
+
+def make_cfg(layer_num, n1, n2, use_space_time, precision="exact", chunk_rays=0):
+    """The cfg fields the model reads (modeling/layered_rfrender.py:23-37) + the two B200 knobs."""
+    M = types.SimpleNamespace(
+        BOARDER_WEIGHT=1e10, SAMPLE_METHOD="BBOX", SAME_SPACENET=False, TKERNEL_INC_RAW=True,
+        POSE_REFINEMENT=False, USE_DIR=True, USE_DEFORM_VIEW=False, USE_DEFORM_TIME=True,
+        USE_SPACE_TIME=use_space_time, BKGD_USE_DEFORM_TIME=False, BKGD_USE_SPACE_TIME=False,
+        DEEP_RGB=False, COARSE_RAY_SAMPLING=n1, FINE_RAY_SAMPLING=n2, B200_PRECISION=precision,
+        B200_CHUNK_RAYS=chunk_rays)
+    return types.SimpleNamespace(MODEL=M, DATASETS=types.SimpleNamespace(LAYER_NUM=layer_num))
+
+
+def build_case_model(name, precision="exact", chunk_rays=0, sd=None):
+    import modeling
+    case = C.CASES[name]
+    sd = sd if sd is not None else C.state_dict_for(case)
+    if sd is None:
+        return None
+    model = modeling.build_layered_model(make_cfg(case["L"], case["n1"], case["n2"], case["space_time"], precision,
+                                                  chunk_rays), 0, case.get("scale"), case.get("shift"))
+    model.load_state_dict(sd)
+    bkgd, frames = C.boxes_for(case)
+    model.set_bkgd_bbox(bkgd)
+    model.set_bboxes(frames)
+    model.near = case.get("near", 0.0)
+    model.alpha = case.get("alpha", 1.0)
+    for i in case.get("hidden", []):
+        model.hide_layer(i)
+    return model.cuda()
+
+
+def run_case_native(name, precision="exact", chunk_rays=0, inject=True, rays=None, uniforms=None):
+    """Render a golden case through the facade (model.forward); returns the flat numpy dict of cases.flatten_outputs."""
+    case = C.CASES[name]
+    model = build_case_model(name, precision, chunk_rays)
+    if model is None:
+        return None
+    rays = C.rays_for(case) if rays is None else rays
+    jit, u = C.uniforms_for(case) if uniforms is None else uniforms
+    dev = torch.device("cuda", 0)
+    if inject:
+        model.inject_uniforms(jit.to(dev), None if u is None else u.to(dev))
+    with torch.no_grad():
+        out = model(rays.to(dev), torch.zeros(rays.shape[0], device=dev), None,
+                    only_coarse=case.get("only_coarse", False), density_threshold=case["thr"][0],
+                    bkgd_density_threshold=case["thr"][1])
+    torch.cuda.synchronize()
+    return C.flatten_outputs(*out)
+
+
+def psnr(a, b):
+    mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)       # utils/metrics.py:16-17
+
+
+def compare(flat, gold, keys=None):
+    """Per-key max abs error + fraction of rays whose rgb error exceeds 1e-3."""
+    rep = {}
+    for k in (keys or gold):
+        if k.startswith("ray_mask"):
+            rep[k] = float((flat[k] != gold[k]).sum())
+        else:
+            rep[k] = float(np.abs(flat[k].astype(np.float64) - gold[k]).max())
+    return rep
