@@ -148,6 +148,10 @@ int stnerf_spacenet(stnerf_handle h, int layer, int fine, const float* pos, cons
 int stnerf_motionnet(stnerf_handle h, int layer, const float* xyzt, int64_t P, int lerp_mode, float* flow,
                      void* stream);
 
+/* Tensor-core plumbing self-test: one 128x128x64 fp16 UMMA through the library's descriptors, swizzled layout, bulk
+ * copy and TMEM load; writes max |D - host reference| (expected < 1e-3).                                     */
+int stnerf_selftest_umma(float* max_err_host);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 uint64_t stnerf_launch_count(void);
 

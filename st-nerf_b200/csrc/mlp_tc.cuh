@@ -16,6 +16,7 @@ struct TcNet {
 int tc_pack_spacenet(TcNet& net, const float* blob_host, bool use_time);
 int tc_pack_motionnet(TcNet& net, const float* blob_host);
 void tc_free(TcNet& net);
+int tc_selftest(float* max_err_host);   // one 128x128x64 UMMA vs a host reference
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* raw,
                        float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st);
 int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW& w32, int precision,

@@ -144,3 +144,12 @@ def test_networks(tag, precision, sig_tol, rgb_tol):
         flow = r.motionnet(1, dev(torch.cat([IN["net.pos"], tcol], 1)))
         close(flow, FN["net.%s.motion_%s" % (tag, kind)], 2e-4, 2e-4, "motion " + kind)
     r.close()
+
+
+def test_umma_selftest():
+    """One 128x128x64 fp16 MMA through the library's UMMA descriptors / SW128 layout / bulk copy / TMEM load."""
+    import ctypes
+    from stnerf_b200 import _lib as L
+    err = ctypes.c_float(-1.0)
+    L.check(L.lib().stnerf_selftest_umma(ctypes.byref(err)), "stnerf_selftest_umma")
+    assert 0.0 <= err.value < 1e-3, err.value
