@@ -37,9 +37,10 @@ def all_gather_planes(local: torch.Tensor, world: int, group=None) -> torch.Tens
     """local (P, n) contiguous -> (world, P, n) on every rank with a single collective."""
     if world == 1:
         return local.unsqueeze(0)
-    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
+    local = local.contiguous()
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)          # concatenation along dim 0 (NCCL and gloo agree)
+    return out.view((world,) + tuple(local.shape))
 
 
 class ShardedViewRenderer:
