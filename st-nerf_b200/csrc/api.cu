@@ -46,6 +46,7 @@ struct stnerf_ctx {
   // workspace (sized for chunk_rays rays, cap_n1 coarse and cap_s2 total samples)
   int cap_n1 = 0, cap_s2 = 0;
   float *t_coarse = nullptr, *raw_coarse = nullptr, *t_fine = nullptr, *raw_fine = nullptr, *xyz = nullptr;
+  float* cbuf = nullptr;       // per-slot rgb_net.1 bias of the SpaceNet being evaluated (tensor-core modes)
   uint8_t* mask_ws = nullptr;
   int *hit = nullptr, *counts = nullptr, *lerp_flags = nullptr;
   size_t ws_bytes = 0;
@@ -80,6 +81,7 @@ struct ProfScope {
 
 static void free_ws(stnerf_ctx* c) {
   cudaFree(c->t_coarse); cudaFree(c->raw_coarse); cudaFree(c->t_fine); cudaFree(c->raw_fine); cudaFree(c->xyz);
+  cudaFree(c->cbuf); c->cbuf = nullptr;
   cudaFree(c->mask_ws); cudaFree(c->hit); cudaFree(c->counts); cudaFree(c->lerp_flags);
   c->t_coarse = c->raw_coarse = c->t_fine = c->raw_fine = c->xyz = nullptr;
   c->mask_ws = nullptr; c->hit = c->counts = c->lerp_flags = nullptr;
@@ -103,6 +105,7 @@ static int ensure_ws(stnerf_ctx* c, int n1, int s2) {
   rc |= A((void**)&c->t_fine, l * R * cs2 * 4);
   rc |= A((void**)&c->raw_fine, l * R * cs2 * 16);
   rc |= A((void**)&c->xyz, R * cs2 * 12);
+  rc |= A((void**)&c->cbuf, R * 128 * 4);
   rc |= A((void**)&c->mask_ws, l * R);
   rc |= A((void**)&c->hit, l * R * 4);
   rc |= A((void**)&c->counts, STNERF_MAX_LAYERS * 4);
@@ -299,7 +302,14 @@ static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, fl
   ProfScope ps(c, 0, (double)src.n_slots * src.S, count_slot, src.S, st);
   if (c->precision == STNERF_PREC_FP32_SIMT)
     return launch_spacenet_simt(src, net.w, raw, 0, rgb, sigma, c->num_sms, st);
-  return tc_launch_spacenet(src, net.tc, net.w, c->precision, raw, rgb, sigma, c->num_sms, st);
+  if (src.mode == SRC_EXPLICIT) {      // unit entry point: one bias row per point, stream-ordered scratch
+    float* cb = nullptr;
+    STNERF_CUDA(cudaMallocAsync((void**)&cb, (size_t)std::max<long long>(src.n_slots, 1) * 128 * sizeof(float), st));
+    const int rc = tc_launch_spacenet(src, net.tc, net.w, c->precision, cb, raw, rgb, sigma, c->num_sms, st);
+    STNERF_CUDA(cudaFreeAsync(cb, st));
+    return rc;
+  }
+  return tc_launch_spacenet(src, net.tc, net.w, c->precision, c->cbuf, raw, rgb, sigma, c->num_sms, st);
 }
 static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, const int* lerp_flag, int lerp_force,
                          float* xyz_out, float* flow_out, cudaStream_t st, int count_slot = -1) {
@@ -336,6 +346,7 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     }
     s.hit = c->hit + (size_t)i * R;
     s.count = c->counts + i;
+    s.n_slots_cap = n;
     rc = run_motionnet(c, s, c->motion[i], c->lerp_flags + i, -1, c->xyz, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
     if (rc) return rc;
     s.mode = SRC_XYZ;

@@ -77,6 +77,7 @@ struct PointSrc {
   const int* hit;            // slot -> ray, or null (identity: background)
   const int* count;          // device-side number of slots, or null
   long long n_slots;         // slots when count == null; P for SRC_EXPLICIT (with S == 1)
+  long long n_slots_cap;     // upper bound on *count (grid sizing of per-slot helper kernels)
   const float* t;            // (rays, S) depths of this layer
   int S;
   int layer;                 // frame id column = 6 + layer

@@ -2,18 +2,23 @@
 //
 // One persistent CTA per SM walks tiles of 128 points.  Per tile the whole network runs on-chip:
 //   * activations (A operand) live in shared memory as fp16 hi/lo pairs in the canonical 128B-swizzled K-major
-//     UMMA layout; they never leave the SM between layers;
-//   * weights (B operand) are pre-packed on the host into 16 KB blocks [128 out-rows x 64 k] that are already the
-//     swizzled shared-memory image, in the exact order the MMA warp consumes them, and stream through a 4-stage
-//     ring with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) from L2;
+//     UMMA layout ([128 rows x 64 k] blocks); they never leave the SM between layers;
+//   * weights (B operand) are pre-packed on the host into [N out-rows x 32 k] fp16 blocks (N = 256 or 128) that are
+//     already the 64B-swizzled shared-memory image, in the exact order the MMA warp consumes them, and stream through
+//     a 4-stage ring with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) from L2;
+//   * every MMA is M=128 x N=256 (or 128) x K=16, so the A tile is re-read from shared memory once per 256 outputs;
 //   * accumulators live in TMEM (two 128x256 fp32 buffers = all 512 columns) so the epilogue of layer k
 //     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1, k-chunk by k-chunk;
 //   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which
 //     reproduces fp32 products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate);
+//   * the input encoding of tile i+1 is written while the tensor core works on the late layers of tile i;
+//   * relu(PE(dir) | PE(time)) enters rgb_net.1 as a per-ray fp32 bias computed by head_bias_kernel
+//     (b1 + W1[:,256:] . relu(enc)), so the last GEMM is a clean K=256;
 //   * the 1-wide density head, the 3-wide rgb / flow heads and all biases are fp32 FFMA work in the epilogue.
 //
 // Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue /
-// encoding warps (warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half of every 64-column chunk).
+// encoding warps: warp%4 selects the TMEM lane quarter (row = 32*(warp%4) + lane), (warp-4)/4 the column half of
+// every 64-column chunk and the half of the encoding frequencies the thread computes for its row.
 //
 // Restates modeling/spacenet.py:101-160, modeling/motion_net.py:34-71, utils/dimension_kernel.py:24-33.
 #include <cuda_fp16.h>
@@ -25,22 +30,20 @@ namespace stnerf {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int BLOCK_BYTES = 16384;           // [128 rows x 64 k] fp16, 128B-swizzled K-major
+constexpr int ABLOCK = 16384;                // activation block [128 rows x 64 k] fp16, SWIZZLE_128B
+constexpr int STAGE_BYTES = 16384;           // weight stage   [256 rows x 32 k] fp16, SWIZZLE_64B (N=128 layers use half)
 constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 384;
-constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8, N_EPI_THREADS = 256;
+constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
 
 // shared memory map (bytes, from a 1024-aligned base)
-constexpr int SM_ACT = 0;                    // 8 blocks: term*4 + kchunk (term 0 = hi, 1 = lo)
-constexpr int SM_ENC = 8 * BLOCK_BYTES;      // 2 blocks: hi, lo (SpaceNet).  MotionNet: ACT = blocks 0-3, ENC = blocks 4-7
-constexpr int SM_RING = 10 * BLOCK_BYTES;    // NSTAGE weight blocks
-constexpr int SM_MISC = SM_RING + NSTAGE * BLOCK_BYTES;
-constexpr int MISC_BAR = 0;                  // mbarriers (8 B each)
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_DFULL = 13, BAR_DEMPTY = 15, N_BARS = 17;
-constexpr int MISC_TMEM = 144;               // tmem base address
-constexpr int MISC_OUTIDX = 160;             // int32[128]
-constexpr int MISC_PART = MISC_OUTIDX + 512; // float[128][4]: partial head sums of column-half 1 (sigma | rgb / flow);
-                                             // MotionNet parks the un-deformed xyz of each row here until the last layer
+constexpr int SM_ACT = 0;                    // 8 blocks
+constexpr int SM_ENC = 8 * ABLOCK;           // 2 blocks: hi, lo (SpaceNet).  MotionNet: ACT = blocks 0-3, ENC = blocks 4-7
+constexpr int SM_RING = 10 * ABLOCK;
+constexpr int SM_MISC = SM_RING + NSTAGE * STAGE_BYTES;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_DFULL = 13, BAR_DEMPTY = 15;
+constexpr int MISC_TMEM = 144;
+constexpr int MISC_PART = 160;               // float[128][4]: head partial sums of column-half 1
 constexpr int SM_TOTAL = SM_MISC + MISC_PART + 2048;
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
@@ -69,8 +72,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the kernel aborts with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
     if (spin > (1u << 26)) {
       printf("stnerf mlp_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
@@ -105,8 +109,7 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -117,23 +120,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// The registers are threaded through the wait so no consumer can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// {lo16 = fp16(a), hi16 = fp16(b)}, saturating to +-65504 (fp16 range guard of the split)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&p));
+}
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout), K-major operands.
+//   A: SWIZZLE_128B, 8-row groups 1024 B apart;  B: SWIZZLE_64B, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// Instruction descriptor: fp16 A/B (K-major), fp32 D, M = 128, N = 128 (cute::UMMA::InstrDescriptor).
-constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// Instruction descriptor: fp16 A/B (K-major), fp32 D, M = 128 (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t idesc_n(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
-// byte offset of element (row, col) of a [128 x 64] fp16 block in the 128B-swizzled K-major layout
+// byte offset of element (row, col) of a [rows x 64] fp16 block, 128B-swizzled K-major (activations)
 __host__ __device__ inline uint32_t sw128_offset(int row, int col) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4) + ((col & 7) << 1));
+}
+// byte offset of element (row, col) of a [rows x 32] fp16 block, 64B-swizzled K-major (weights)
+__host__ __device__ inline uint32_t sw64_offset(int row, int col) {
+  return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((col >> 3) ^ ((row >> 1) & 3)) & 3) << 4) + ((col & 7) << 1));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -144,44 +170,40 @@ enum { NET_SPACE = 0, NET_MOTION = 1 };
 template <int NET> struct Sched;
 template <> struct Sched<NET_SPACE> {
   static constexpr int N_LAYERS = 8;
-  static constexpr int ACT_CHUNKS = 4;                      // 256-wide activations
-  static constexpr int ENC_CHUNKS = 1;
   static constexpr int act_base = SM_ACT, enc_base = SM_ENC;
-  static constexpr int LO_STRIDE = 4 * BLOCK_BYTES;         // ACT lo blocks follow the 4 hi blocks
-  static constexpr int ENC_LO_STRIDE = BLOCK_BYTES;
-  __host__ __device__ static constexpr int n_halves(int l) { return l == 7 ? 1 : 2; }
-  // k-chunk sources of layer l: act chunks used (0 or 4) then enc chunks used (0 or 1)
+  static constexpr int LO_STRIDE = 4 * ABLOCK;          // ACT lo blocks follow the 4 hi blocks
+  static constexpr int ENC_LO_STRIDE = ABLOCK;
+  static constexpr int ENC_LAST_USE = 4;                // last layer whose MMAs read the encoding buffer
+  __host__ __device__ static constexpr int n_out(int l) { return l == 7 ? 128 : 256; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 4; }
-  __host__ __device__ static constexpr int enc_chunks(int l) { return (l == 0 || l == 4 || l == 7) ? 1 : 0; }
-  __host__ __device__ static constexpr bool enc_needs_wait(int l) { return l == 0 || l == 7; }
+  __host__ __device__ static constexpr int enc_chunks(int l) { return (l == 0 || l == 4) ? 1 : 0; }
 };
 template <> struct Sched<NET_MOTION> {
   static constexpr int N_LAYERS = 5;
-  static constexpr int ACT_CHUNKS = 2;                      // 128-wide activations
-  static constexpr int ENC_CHUNKS = 2;                      // PE(84) padded to 128
-  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * BLOCK_BYTES;
-  static constexpr int LO_STRIDE = 2 * BLOCK_BYTES;
-  static constexpr int ENC_LO_STRIDE = 2 * BLOCK_BYTES;
-  __host__ __device__ static constexpr int n_halves(int) { return 1; }
+  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * ABLOCK;
+  static constexpr int LO_STRIDE = 2 * ABLOCK;
+  static constexpr int ENC_LO_STRIDE = 2 * ABLOCK;
+  static constexpr int ENC_LAST_USE = 0;
+  __host__ __device__ static constexpr int n_out(int) { return 128; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 2; }
   __host__ __device__ static constexpr int enc_chunks(int l) { return l == 0 ? 2 : 0; }
-  __host__ __device__ static constexpr bool enc_needs_wait(int l) { return l == 0; }
 };
 
 template <int NET>
-__host__ __device__ constexpr int blocks_per_tile() {
-  int n = 0;
+__host__ __device__ constexpr size_t stream_bytes_per_tile() {
+  size_t n = 0;
   for (int l = 0; l < Sched<NET>::N_LAYERS; ++l)
-    n += (Sched<NET>::act_chunks(l) + Sched<NET>::enc_chunks(l)) * Sched<NET>::n_halves(l) * 2;
+    n += (size_t)(Sched<NET>::act_chunks(l) + Sched<NET>::enc_chunks(l)) * 2 /*sub-chunks*/ * 2 /*hi,lo*/ *
+         Sched<NET>::n_out(l) * 64;
   return n;
 }
 
 struct TcParams {
   PointSrc src;
-  const uint8_t* wblocks;     // packed weight stream (hi/lo blocks in consumption order)
-  const float* aux;           // fp32: biases per layer [8][256] | w_sigma[256] | b_sigma | w_out[3][128] | b_out[3]
+  const uint8_t* wstream;     // packed weight stream (hi/lo stages in consumption order)
+  const float* aux;           // fp32: biases [8][256] | w_sigma[256] | b_sigma | w_out[3][128] | b_out[3]
+  const float* cbuf;          // SpaceNet: per-slot rgb_net.1 bias (b1 + W1[:,256:].relu(enc(dir,time))), [slots][128]
   int exact;                  // 1: 3-term split, 0: single fp16 pass
-  int use_time;
   // outputs
   float* raw;                 // float4 per sample (pipeline mode)
   float* rgb_out;             // explicit mode
@@ -198,35 +220,36 @@ constexpr int AUX_BIAS = 0, AUX_WSIG = 8 * 256, AUX_BSIG = AUX_WSIG + 256, AUX_W
 // ---------------------------------------------------------------------------------------------------------
 // point fetch (same arithmetic as mlp_simt.cu::fetch_point)
 // ---------------------------------------------------------------------------------------------------------
-struct Pt { float x, y, z, dx, dy, dz, tm; int out_index; };
+struct Pt { float x, y, z, tm; int out_index; int cidx; };
 
 __device__ __forceinline__ Pt fetch_pt(const PointSrc& s, long long p, long long n_points) {
   Pt q;
-  q.x = q.y = q.z = q.dx = q.dy = q.dz = q.tm = 0.f;
+  q.x = q.y = q.z = q.tm = 0.f;
   q.out_index = -1;
+  q.cidx = 0;
   if (p >= n_points) return q;
   if (s.mode == SRC_EXPLICIT) {
     const float* pp = s.pos + p * s.pos_stride;
     q.x = pp[0]; q.y = pp[1]; q.z = pp[2];
-    if (s.dirs) { q.dx = s.dirs[3 * p]; q.dy = s.dirs[3 * p + 1]; q.dz = s.dirs[3 * p + 2]; }
     if (s.times) q.tm = s.times[p * s.time_stride];
     q.out_index = (int)p;
+    q.cidx = (int)p;
     return q;
   }
   const long long slot = p / s.S;
   const int k = (int)(p - slot * s.S);
   const long long ray = s.hit ? (long long)s.hit[slot] : slot;
   const float* rp = s.rays + ray * s.ray_stride;
-  q.dx = rp[3]; q.dy = rp[4]; q.dz = rp[5];
   q.tm = rp[6 + s.layer];
   q.out_index = (int)(ray * s.S + k);
+  q.cidx = (int)slot;
   if (s.mode == SRC_XYZ) {
     q.x = s.pos[3 * p]; q.y = s.pos[3 * p + 1]; q.z = s.pos[3 * p + 2];
     return q;
   }
   const float tt = s.t[ray * s.S + k];
-  float v[3] = {__fadd_rn(__fmul_rn(tt, q.dx), rp[0]), __fadd_rn(__fmul_rn(tt, q.dy), rp[1]),
-                __fadd_rn(__fmul_rn(tt, q.dz), rp[2])};
+  float v[3] = {__fadd_rn(__fmul_rn(tt, rp[3]), rp[0]), __fadd_rn(__fmul_rn(tt, rp[4]), rp[1]),
+                __fadd_rn(__fmul_rn(tt, rp[5]), rp[2])};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     if (s.shift_on) v[a] = __fsub_rn(v[a], s.shift[a]);
@@ -236,53 +259,99 @@ __device__ __forceinline__ Pt fetch_pt(const PointSrc& s, long long p, long long
   return q;
 }
 
-// store one fp32 value as fp16 hi (+ lo) at element (row, col) of a hi block / its lo twin
-__device__ __forceinline__ void put_split(uint8_t* hi_block, int lo_stride, int row, int col, float v, bool exact) {
-  const __half h = __float2half_rn(v);
-  const uint32_t off = sw128_offset(row, col);
-  *reinterpret_cast<__half*>(hi_block + off) = h;
-  if (exact) *reinterpret_cast<__half*>(hi_block + lo_stride + off) = __float2half_rn(v - __half2float(h));
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// epilogue helpers
-// ---------------------------------------------------------------------------------------------------------
-// 32 accumulator columns of one row -> bias + ReLU -> fp16 hi/lo -> four 16-byte stores each.
-// `dotw` (optional): fp32 head weights for these 32 columns, accumulated into dot[0..ND).
-template <int ND>
-__device__ __forceinline__ void epi_store32(const float (&acc)[32], const float* __restrict__ bias, uint8_t* hi_blk,
-                                            int lo_stride, int row, int col0, bool exact,
-                                            const float* __restrict__ dotw, int dotw_stride, float (&dot)[ND > 0 ? ND : 1]) {
+// Write NV fp32 values of one row as fp16 hi (+lo) 16-byte chunks: columns col0 .. col0+NV-1 of an activation block
+// (col0 and NV multiples of 8).
+template <int NV>
+__device__ __forceinline__ void store_row_split(uint8_t* hi_blk, int lo_stride, int row, int col0, const float (&v)[NV],
+                                                bool exact) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {               // 8 columns -> one 16-byte chunk
+  for (int g = 0; g < NV / 8; ++g) {
     uint32_t hp[4], lp[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = g * 8 + e * 2;
-      float v0 = fmaxf(acc[c] + __ldg(bias + c), 0.f);
-      float v1 = fmaxf(acc[c + 1] + __ldg(bias + c + 1), 0.f);
-      v0 = fminf(v0, 65504.f); v1 = fminf(v1, 65504.f);
-      if (ND > 0) {
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          dot[d] = fmaf(v0, __ldg(dotw + d * dotw_stride + c), dot[d]);
-          dot[d] = fmaf(v1, __ldg(dotw + d * dotw_stride + c + 1), dot[d]);
-        }
-      }
-      const __half2 h = __floats2half2_rn(v0, v1);
-      hp[e] = *reinterpret_cast<const uint32_t*>(&h);
-      if (exact) {
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-        lp[e] = *reinterpret_cast<const uint32_t*>(&l);
-      }
+      const float a = v[g * 8 + 2 * e], b = v[g * 8 + 2 * e + 1];
+      hp[e] = pack_f16x2(a, b);
+      const float2 hf = unpack_f16x2(hp[e]);
+      lp[e] = pack_f16x2(a - hf.x, b - hf.y);
     }
-    if (hi_blk) {
-      const uint32_t off = sw128_offset(row, col0 + g * 8);
-      *reinterpret_cast<uint4*>(hi_blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-      if (exact) *reinterpret_cast<uint4*>(hi_blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-    }
+    const uint32_t off = sw128_offset(row, col0 + g * 8);
+    *reinterpret_cast<uint4*>(hi_blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    if (exact) *reinterpret_cast<uint4*>(hi_blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
+}
+
+// Input encoding of one row, written by the two threads (half = 0/1) that own the row.
+// Column order is a permutation of the reference's (utils/dimension_kernel.py:24-33) chosen so each thread owns whole
+// 16-byte chunks; the weight packer applies the same permutation (enc_perm_* below).
+//   SpaceNet (64 cols):  half 0 -> [x, y, f0..f4: sin xyz, cos xyz]   half 1 -> [z, f5..f9: sin xyz, cos xyz, 0]
+//   MotionNet (2 x 64):  half 0 -> chunk 0 [x,y,z,t, f0..f4: sin xyzt, cos xyzt, 0 x20]   half 1 -> chunk 1 [f5..f9 ..., 0 x24]
+template <int NET, int half>
+__device__ __forceinline__ void encode_row_half(uint8_t* smem, const Pt& pt, int row, bool exact, bool lerp) {
+  using S = Sched<NET>;
+  uint8_t* enc = smem + S::enc_base;
+  if (NET == NET_SPACE) {
+    const float xs[3] = {pt.x, pt.y, pt.z};
+    float v[32];
+    int n = 0;
+    if (half == 0) { v[0] = xs[0]; v[1] = xs[1]; n = 2; } else { v[0] = xs[2]; n = 1; }
+#pragma unroll
+    for (int ff = 0; ff < 5; ++ff) {
+      const float fr = (float)(1 << (half * 5 + ff));
+      float sn[3], cs[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sincosf(xs[d] * fr, &sn[d], &cs[d]);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { v[n + d] = sn[d]; v[n + 3 + d] = cs[d]; }
+      n += 6;
+    }
+    if (half == 1) v[31] = 0.f;
+    store_row_split<32>(enc, S::ENC_LO_STRIDE, row, half * 32, v, exact);
+  } else {
+    const float lo_t = floorf(pt.tm), wgt = pt.tm - lo_t, omw = 1.0f - wgt;
+    const float in4[4] = {pt.x, pt.y, pt.z, pt.tm};
+    float v[64];
+    int n = 0;
+    if (half == 0) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        float a = in4[d];
+        if (lerp) {      // (1-w)*PE([xyz, floor t]) + w*PE([xyz, floor t + 1]) column by column (motion_net.py:63)
+          const float lo = d < 3 ? in4[d] : lo_t, hi = d < 3 ? in4[d] : lo_t + 1.0f;
+          a = __fadd_rn(__fmul_rn(omw, lo), __fmul_rn(wgt, hi));
+        }
+        v[d] = a;
+      }
+      n = 4;
+    }
+#pragma unroll
+    for (int ff = 0; ff < 5; ++ff) {
+      const float fr = (float)(1 << (half * 5 + ff));
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        float sn, cs;
+        if (!lerp) {
+          sincosf(in4[d] * fr, &sn, &cs);
+        } else {
+          const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? a : lo_t + 1.0f;
+          float s0, c0, s1, c1;
+          sincosf(a * fr, &s0, &c0);
+          sincosf(b2 * fr, &s1, &c1);
+          sn = __fadd_rn(__fmul_rn(omw, s0), __fmul_rn(wgt, s1));
+          cs = __fadd_rn(__fmul_rn(omw, c0), __fmul_rn(wgt, c1));
+        }
+        v[n + d] = sn; v[n + 4 + d] = cs;
+      }
+      n += 8;
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) if (i >= (half == 0 ? 44 : 40)) v[i] = 0.f;
+    store_row_split<64>(enc + half * ABLOCK, S::ENC_LO_STRIDE, row, 0, v, exact);
+  }
+}
+template <int NET>
+__device__ __forceinline__ void encode_row(uint8_t* smem, const Pt& pt, int row, int half, bool exact, bool lerp) {
+  if (half == 0) encode_row_half<NET, 0>(smem, pt, row, exact, lerp);
+  else encode_row_half<NET, 1>(smem, pt, row, exact, lerp);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -293,14 +362,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
   using S = Sched<NET>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  if ((sbase & 1023u) != 0) {                    // SWIZZLE_128B operands need a 1024-byte aligned base
+  if ((sbase & 1023u) != 0) {                    // swizzled operands need a 1024-byte aligned base
     if (threadIdx.x == 0) printf("stnerf mlp_tc: dynamic shared memory base %u is not 1024-byte aligned\n", sbase);
     __trap();
   }
-  const uint32_t bars = sbase + SM_MISC + MISC_BAR;
+  const uint32_t bars = sbase + SM_MISC;
   auto BAR = [bars](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC + MISC_TMEM);
-  int* s_outidx = reinterpret_cast<int*>(smem + SM_MISC + MISC_OUTIDX);
   float* s_part = reinterpret_cast<float*>(smem + SM_MISC + MISC_PART);     // [128][4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -325,27 +393,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
     if (lane == 0) {
       uint32_t cnt = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int blk = 0;
+        const uint8_t* src = P.wstream;
         for (int l = 0; l < S::N_LAYERS; ++l) {
-          const int nch = S::act_chunks(l) + S::enc_chunks(l), nh = S::n_halves(l);
-          for (int c = 0; c < nch; ++c)
-            for (int term = 0; term < 2; ++term)
-              for (int h = 0; h < nh; ++h, ++blk) {
-                if (term == 1 && !exact) continue;           // fast mode never touches the lo blocks
-                const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
-                mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
-                mbar_expect_tx(BAR(BAR_WFULL + s), BLOCK_BYTES);
-                bulk_g2s(sbase + SM_RING + s * BLOCK_BYTES, P.wblocks + (size_t)blk * BLOCK_BYTES, BLOCK_BYTES,
-                         BAR(BAR_WFULL + s));
-                ++cnt;
-              }
+          const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
+          const uint32_t bytes = (uint32_t)S::n_out(l) * 64;
+          for (int sc = 0; sc < nsub; ++sc)
+            for (int term = 0; term < 2; ++term, src += bytes) {
+              if (term == 1 && !exact) continue;             // fast mode never touches the lo stages
+              const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
+              mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
+              mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
+              bulk_g2s(sbase + SM_RING + s * STAGE_BYTES, src, bytes, BAR(BAR_WFULL + s));
+              ++cnt;
+            }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      uint32_t cnt = 0;            // weight blocks consumed
+      uint32_t cnt = 0;            // weight stages consumed
       uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
       uint32_t a_uses[5] = {0, 0, 0, 0, 0};
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -353,42 +420,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
           const uint32_t b = g & 1;
           mbar_wait(BAR(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);      // accumulator buffer drained (layer g-2)
           tc_fence_after();
-          const uint32_t dcol = tmem_base + b * 256;
-          const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l), nh = S::n_halves(l);
+          const uint32_t d = tmem_base + b * 256;
+          const uint32_t idesc = idesc_n((uint32_t)S::n_out(l));
+          const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
             if (c < nact) {
-              a_hi = sbase + S::act_base + c * BLOCK_BYTES;
+              a_hi = sbase + S::act_base + c * ABLOCK;
               a_lo = a_hi + S::LO_STRIDE;
               mbar_wait(BAR(BAR_AREADY + c), a_uses[c] & 1);
               ++a_uses[c];
             } else {
               const int e = c - nact;
-              a_hi = sbase + S::enc_base + e * BLOCK_BYTES;
+              a_hi = sbase + S::enc_base + e * ABLOCK;
               a_lo = a_hi + S::ENC_LO_STRIDE;
-              if (S::enc_needs_wait(l) && e == 0) {                // one arrival phase covers every enc chunk
+              if (l == 0 && e == 0) {                              // one arrival phase per tile covers the whole encoding
                 mbar_wait(BAR(BAR_AREADY + 4), a_uses[4] & 1);
                 ++a_uses[4];
               }
             }
             tc_fence_after();
-            for (int term = 0; term < 2; ++term) {
-              if (term == 1 && !exact) continue;
-              for (int h = 0; h < nh; ++h) {
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
+              for (int term = 0; term < 2; ++term) {
+                if (term == 1 && !exact) continue;
                 const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
                 mbar_wait(BAR(BAR_WFULL + s), n & 1);
                 tc_fence_after();
-                const uint32_t wsm = sbase + SM_RING + s * BLOCK_BYTES;
-                const uint32_t d = dcol + h * 128;
-                // hi block: D += Ahi*Whi (+ Alo*Whi);  lo block: D += Ahi*Wlo
+                const uint32_t wsm = sbase + SM_RING + s * STAGE_BYTES;
+                // hi stage: D += Ahi*Whi (+ Alo*Whi);  lo stage: D += Ahi*Wlo
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wsm + ks * 32), IDESC_N128,
-                           (c == 0 && term == 0 && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < 2; ++ks)
+                  umma_f16(d, make_desc_sw128(a_hi + a_off + ks * 32), make_desc_sw64(wsm + ks * 32), idesc,
+                           (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
                 if (term == 0 && exact) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_f16(d, make_desc(a_lo + ks * 32), make_desc(wsm + ks * 32), IDESC_N128, 1u);
+                  for (int ks = 0; ks < 2; ++ks)
+                    umma_f16(d, make_desc_sw128(a_lo + a_off + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, 1u);
                 }
                 umma_commit(BAR(BAR_WEMPTY + s));                   // ring slot reusable once these MMAs retire
                 ++cnt;
@@ -402,202 +470,156 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
   } else if (warp >= EPI_WARP0) {
     // =============================== encoding + epilogue warps ===============================
     const int ew = warp - EPI_WARP0;            // 0..7
-    const int q = ew & 3, hh = ew >> 2;         // TMEM lane quarter, column half
-    const int row = q * 32 + lane;              // accumulator row owned in the epilogue
+    const int q = ew & 3, hh = ew >> 2;         // TMEM lane quarter, column half / encoding half
+    const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* bias_all = P.aux + AUX_BIAS;
-    // encoding phase mapping: two adjacent lanes share a row
-    const int erow = ew * 16 + (lane >> 1), epar = lane & 1;
+    const bool lerp = (NET == NET_MOTION) && (P.lerp_force >= 0 ? (P.lerp_force != 0) : (P.lerp_flag && *P.lerp_flag != 0));
     uint32_t g = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      // ---- fetch the tile's points and write the input encoding ----
-      const Pt pt = fetch_pt(P.src, tile * TILE_M + erow, n_points);
-      if (epar == 0) s_outidx[erow] = pt.out_index;
-      uint8_t* enc_hi = smem + S::enc_base;
-      if (NET == NET_SPACE) {
-        // PE(pos, L=10): col 0..2 raw, 3+6f+d sin, 6+6f+d cos (utils/dimension_kernel.py:24-33); col 63 = 0
-        const float xs[3] = {pt.x, pt.y, pt.z};
-        if (epar == 0) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) put_split(enc_hi, S::ENC_LO_STRIDE, erow, d, xs[d], exact);
-        } else {
-          put_split(enc_hi, S::ENC_LO_STRIDE, erow, 63, 0.f, exact);
-        }
-#pragma unroll
-        for (int ff = 0; ff < 5; ++ff) {
-          const int f = epar * 5 + ff;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float sn, cs;
-            sincosf(xs[d] * (float)(1 << f), &sn, &cs);
-            put_split(enc_hi, S::ENC_LO_STRIDE, erow, 3 + 6 * f + d, sn, exact);
-            put_split(enc_hi, S::ENC_LO_STRIDE, erow, 6 + 6 * f + d, cs, exact);
-          }
-        }
-      } else {
-        // PE([x,y,z,t], L=10) (+ the reference's lerp of the encodings of floor(t), floor(t)+1, motion_net.py:48-63)
-        const bool lerp = P.lerp_force >= 0 ? (P.lerp_force != 0) : (P.lerp_flag && *P.lerp_flag != 0);
-        const float lo_t = floorf(pt.tm), wgt = pt.tm - lo_t, omw = 1.0f - wgt;
-        const float in4[4] = {pt.x, pt.y, pt.z, pt.tm};
-        if (epar == 0) {
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            float v = in4[d];
-            if (lerp) {
-              const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? in4[d] : lo_t + 1.0f;
-              v = __fadd_rn(__fmul_rn(omw, a), __fmul_rn(wgt, b2));
-            }
-            put_split(enc_hi, S::ENC_LO_STRIDE, erow, d, v, exact);
-          }
-        }
-        // zero padding columns 84..127 (second enc chunk, cols 20..63)
-        for (int c = 20 + epar; c < 64; c += 2) put_split(enc_hi + BLOCK_BYTES, S::ENC_LO_STRIDE, erow, c, 0.f, exact);
-#pragma unroll
-        for (int ff = 0; ff < 5; ++ff) {
-          const int f = epar * 5 + ff;
-          const float fr = (float)(1 << f);
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            float sn, cs;
-            if (!lerp) {
-              sincosf(in4[d] * fr, &sn, &cs);
-            } else {
-              const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? a : lo_t + 1.0f;
-              float s0, c0, s1, c1;
-              sincosf(a * fr, &s0, &c0);
-              sincosf(b2 * fr, &s1, &c1);
-              sn = __fadd_rn(__fmul_rn(omw, s0), __fmul_rn(wgt, s1));
-              cs = __fadd_rn(__fmul_rn(omw, c0), __fmul_rn(wgt, c1));
-            }
-            const int cs_col = 4 + 8 * f + d, cc_col = 8 + 8 * f + d;
-            put_split(enc_hi + (cs_col >> 6) * BLOCK_BYTES, S::ENC_LO_STRIDE, erow, cs_col & 63, sn, exact);
-            put_split(enc_hi + (cc_col >> 6) * BLOCK_BYTES, S::ENC_LO_STRIDE, erow, cc_col & 63, cs, exact);
-          }
-        }
-      }
+
+    // encoding of the first tile
+    Pt cur = fetch_pt(P.src, (long long)blockIdx.x * TILE_M + row, n_points);
+    if ((long long)blockIdx.x < n_tiles) {
+      encode_row<NET>(smem, cur, row, hh, exact, lerp);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
-      // MotionNet keeps the un-deformed position of the epilogue row for the final xyz + flow
-      float my_xyz[3] = {0.f, 0.f, 0.f};
-      if (NET == NET_MOTION) {
-        float* s_xyz = s_part;                  // [128][4] reused: written now, read in the last epilogue
-        if (epar == 0) { s_xyz[erow * 4 + 0] = pt.x; s_xyz[erow * 4 + 1] = pt.y; s_xyz[erow * 4 + 2] = pt.z; }
-      }
-
-      float sig_dot[1] = {0.f};
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      Pt nxt = cur;
+      float sig_dot = 0.f;
       for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
         const uint32_t b = g & 1;
-        mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
-        tc_fence_after();
-        const uint32_t dcol = lane_taddr + b * 256;
         const bool last = (l == S::N_LAYERS - 1);
-        if (NET == NET_SPACE && l == 4) {
-          // MMAs of layer 4 are done with the position encoding: overwrite it with relu(PE(dir) | PE(time))
-          // (modeling/spacenet.py:141-149 and the leading ReLU of rgb_net, :82); cols 27/48..63 = 0
-          const float ds[3] = {pt.dx, pt.dy, pt.dz};
-          const int ntime = P.use_time ? PE_TIME : 0;
-          if (epar == 0) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) put_split(enc_hi, S::ENC_LO_STRIDE, erow, d, fmaxf(ds[d], 0.f), exact);
-            if (P.use_time) put_split(enc_hi, S::ENC_LO_STRIDE, erow, PE_DIR, fmaxf(pt.tm, 0.f), exact);
-          }
-          for (int c = PE_DIR + ntime + epar; c < 64; c += 2) put_split(enc_hi, S::ENC_LO_STRIDE, erow, c, 0.f, exact);
-#pragma unroll
-          for (int ff = 0; ff < 2; ++ff) {
-            const int f = epar * 2 + ff;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              float sn, cs;
-              sincosf(ds[d] * (float)(1 << f), &sn, &cs);
-              put_split(enc_hi, S::ENC_LO_STRIDE, erow, 3 + 6 * f + d, fmaxf(sn, 0.f), exact);
-              put_split(enc_hi, S::ENC_LO_STRIDE, erow, 6 + 6 * f + d, fmaxf(cs, 0.f), exact);
-            }
-          }
-          if (P.use_time) {
-#pragma unroll
-            for (int ff = 0; ff < 5; ++ff) {
-              const int f = epar * 5 + ff;
-              float sn, cs;
-              sincosf(pt.tm * (float)(1 << f), &sn, &cs);
-              put_split(enc_hi, S::ENC_LO_STRIDE, erow, PE_DIR + 1 + 2 * f, fmaxf(sn, 0.f), exact);
-              put_split(enc_hi, S::ENC_LO_STRIDE, erow, PE_DIR + 2 + 2 * f, fmaxf(cs, 0.f), exact);
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
-        }
-        const int width = S::n_halves(l) * 128;                  // output features of this layer
+        const int width = S::n_out(l);
         const float* bias = bias_all + l * 256;
+        const uint32_t dcol = lane_taddr + b * 256;
         if (!last) {
           const bool sigma_layer = (NET == NET_SPACE && l == 6);
+          // bias of the first chunk is fetched before the accumulator wait
+          float4 bv[8];
+          {
+            const float4* bp = reinterpret_cast<const float4*>(bias + hh * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+          }
+          mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
+          tc_fence_after();
           for (int j = 0; j < width / 64; ++j) {                 // 64-column chunk j -> ACT k-chunk j
-            float acc[32];
+            uint32_t acc[32];
             const int col0 = j * 64 + hh * 32;
-            tmem_ld32(dcol + (uint32_t)col0, acc);
-            uint8_t* blk = smem + S::act_base + j * BLOCK_BYTES;
-            if (sigma_layer) {
-              epi_store32<1>(acc, bias + col0, blk, S::LO_STRIDE, row, hh * 32, exact, P.aux + AUX_WSIG + col0, 0, sig_dot);
-            } else {
-              float dummy[1];
-              epi_store32<0>(acc, bias + col0, blk, S::LO_STRIDE, row, hh * 32, exact, nullptr, 0, dummy);
+            tmem_ld32_issue(dcol + (uint32_t)col0, acc);
+            float4 bn[8];
+            if (j + 1 < width / 64) {                            // next chunk's bias while the TMEM load is in flight
+              const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 64);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bn[i] = __ldg(bp + i);
+            }
+            tmem_ld_wait(acc);
+            uint8_t* blk = smem + S::act_base + j * ABLOCK;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {                     // 8 columns -> one 16-byte chunk
+              uint32_t hp[4], lp[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = gq * 8 + e * 2;
+                const float4 bb = bv[c >> 2];
+                const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
+                const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
+                const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
+                if (sigma_layer) {
+                  sig_dot = fmaf(v0, __ldg(P.aux + AUX_WSIG + col0 + c), sig_dot);
+                  sig_dot = fmaf(v1, __ldg(P.aux + AUX_WSIG + col0 + c + 1), sig_dot);
+                }
+                hp[e] = pack_f16x2(v0, v1);
+                if (exact) {
+                  const float2 hf = unpack_f16x2(hp[e]);
+                  lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
+                }
+              }
+              const uint32_t off = sw128_offset(row, hh * 32 + gq * 8);
+              *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+              if (exact) *reinterpret_cast<uint4*>(blk + S::LO_STRIDE + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(BAR_AREADY + j));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bv[i] = bn[i];
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
+          if (l == S::ENC_LAST_USE) {
+            // the MMAs of this layer were the last readers of the encoding buffer (their completion was observed through
+            // d_full above): write the next tile's encoding now, overlapped with the MMAs of the following layers
+            const long long nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+              nxt = fetch_pt(P.src, nt * TILE_M + row, n_points);
+              encode_row<NET>(smem, nxt, row, hh, exact, lerp);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+            }
+          }
         } else {
-          // last layer: 128 features -> 3-wide head in fp32 (rgb_net.3 / motion_net.10), no activation store
+          // last layer: 128 features -> 3-wide head in fp32 (rgb_net.3 / motion_net.10).
+          // SpaceNet: the bias is the per-ray vector of head_bias_kernel (dir/time part of rgb_net.1 + b1).
+          const float* brow = (NET == NET_SPACE) ? (P.cbuf + (size_t)cur.cidx * 128) : bias;
+          mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
+          tc_fence_after();
           float dot3[3] = {0.f, 0.f, 0.f};
           for (int j = 0; j < 2; ++j) {
-            float acc[32];
+            uint32_t acc[32];
             const int col0 = j * 64 + hh * 32;
-            tmem_ld32(dcol + (uint32_t)col0, acc);
-            epi_store32<3>(acc, bias + col0, nullptr, 0, row, 0, exact, P.aux + AUX_WOUT + col0, 128, dot3);
+            tmem_ld32_issue(dcol + (uint32_t)col0, acc);
+            float4 bb4[8];
+            const float4* bp = reinterpret_cast<const float4*>(brow + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bb4[i] = __ldg(bp + i);
+            tmem_ld_wait(acc);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float4 bb = bb4[c >> 2];
+              const float bc = (c & 3) == 0 ? bb.x : (c & 3) == 1 ? bb.y : (c & 3) == 2 ? bb.z : bb.w;
+              const float v = fmaxf(__uint_as_float(acc[c]) + bc, 0.f);
+#pragma unroll
+              for (int o = 0; o < 3; ++o) dot3[o] = fmaf(v, __ldg(P.aux + AUX_WOUT + o * 128 + col0 + c), dot3[o]);
+            }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
           // combine the two column halves through shared memory
-          if (NET == NET_MOTION) {
-            epi_bar_sync();     // the xyz parked by the encoding phase (other warps) is visible from here on
-            my_xyz[0] = s_part[row * 4 + 0]; my_xyz[1] = s_part[row * 4 + 1]; my_xyz[2] = s_part[row * 4 + 2];
-          }
-          epi_bar_sync();
           if (hh == 1) {
             s_part[row * 4 + 0] = dot3[0]; s_part[row * 4 + 1] = dot3[1]; s_part[row * 4 + 2] = dot3[2];
-            s_part[row * 4 + 3] = sig_dot[0];
+            s_part[row * 4 + 3] = sig_dot;
           }
           epi_bar_sync();
-          if (hh == 0) {
-            const int oi = s_outidx[row];
-            if (oi >= 0) {
-              const float o0 = dot3[0] + s_part[row * 4 + 0] + P.aux[AUX_BOUT + 0];
-              const float o1 = dot3[1] + s_part[row * 4 + 1] + P.aux[AUX_BOUT + 1];
-              const float o2 = dot3[2] + s_part[row * 4 + 2] + P.aux[AUX_BOUT + 2];
-              if (NET == NET_SPACE) {
-                const float sg = sig_dot[0] + s_part[row * 4 + 3] + P.aux[AUX_BSIG];
-                if (P.raw) reinterpret_cast<float4*>(P.raw)[oi] = make_float4(o0, o1, o2, sg);
-                if (P.rgb_out) { P.rgb_out[3 * (size_t)oi] = o0; P.rgb_out[3 * (size_t)oi + 1] = o1; P.rgb_out[3 * (size_t)oi + 2] = o2; }
-                if (P.sigma_out) P.sigma_out[oi] = sg;
-              } else {
-                const long long p = tile * TILE_M + row;          // compact point index
-                if (P.flow_out) { P.flow_out[3 * p] = o0; P.flow_out[3 * p + 1] = o1; P.flow_out[3 * p + 2] = o2; }
-                if (P.xyz_out) {
-                  P.xyz_out[3 * p] = __fadd_rn(my_xyz[0], o0);
-                  P.xyz_out[3 * p + 1] = __fadd_rn(my_xyz[1], o1);
-                  P.xyz_out[3 * p + 2] = __fadd_rn(my_xyz[2], o2);
-                }
+          if (hh == 0 && cur.out_index >= 0) {
+            const float o0 = dot3[0] + s_part[row * 4 + 0] + P.aux[AUX_BOUT + 0];
+            const float o1 = dot3[1] + s_part[row * 4 + 1] + P.aux[AUX_BOUT + 1];
+            const float o2 = dot3[2] + s_part[row * 4 + 2] + P.aux[AUX_BOUT + 2];
+            const int oi = cur.out_index;
+            if (NET == NET_SPACE) {
+              const float sg = sig_dot + s_part[row * 4 + 3] + P.aux[AUX_BSIG];
+              if (P.raw) reinterpret_cast<float4*>(P.raw)[oi] = make_float4(o0, o1, o2, sg);
+              if (P.rgb_out) { P.rgb_out[3 * (size_t)oi] = o0; P.rgb_out[3 * (size_t)oi + 1] = o1; P.rgb_out[3 * (size_t)oi + 2] = o2; }
+              if (P.sigma_out) P.sigma_out[oi] = sg;
+            } else {
+              const long long p = tile * TILE_M + row;          // compact point index
+              if (P.flow_out) { P.flow_out[3 * p] = o0; P.flow_out[3 * p + 1] = o1; P.flow_out[3 * p + 2] = o2; }
+              if (P.xyz_out) {                                  // layered_rfrender.py:356 / :510
+                P.xyz_out[3 * p] = __fadd_rn(cur.x, o0);
+                P.xyz_out[3 * p + 1] = __fadd_rn(cur.y, o1);
+                P.xyz_out[3 * p + 2] = __fadd_rn(cur.z, o2);
               }
             }
           }
-          epi_bar_sync();       // s_part / s_outidx are rewritten by the next tile
+          epi_bar_sync();       // s_part is rewritten by the next tile
         }
       }
+      cur = nxt;
     }
   }
   // teardown
@@ -607,14 +629,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// self-test: one 128x128x64 fp16 UMMA through exactly the descriptors / swizzle / TMEM load used above
+// per-slot bias of rgb_net.1: c[slot][n] = b1[n] + sum_k W1[n][256+k] * relu(enc_k(dir, time))   (fp32)
+// (modeling/spacenet.py:141-152 with the leading ReLU of rgb_net, :82; enc = [PE(dir, L=4) (27) | PE(time, L=10) (21)])
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* __restrict__ A, const uint8_t* __restrict__ Bblk,
+constexpr int HB_SLOTS = 8;
+__global__ void __launch_bounds__(128) head_bias_kernel(PointSrc src, const float* __restrict__ w_tail /*[48][128]*/,
+                                                        const float* __restrict__ b1, int use_time,
+                                                        float* __restrict__ cbuf) {
+  __shared__ float s_enc[HB_SLOTS][48];
+  const long long n_slots = src.count ? (long long)(*src.count) : src.n_slots;
+  const int nk = PE_DIR + (use_time ? PE_TIME : 0);
+  const int tid = threadIdx.x;
+  float w[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) w[k] = (k < nk) ? __ldg(w_tail + k * 128 + tid) : 0.f;
+  const float bias = __ldg(b1 + tid);
+  for (long long s0 = (long long)blockIdx.x * HB_SLOTS; s0 < n_slots; s0 += (long long)gridDim.x * HB_SLOTS) {
+    __syncthreads();
+    // thread (sl, j): encoding entry j of slot s0+sl
+    for (int e = tid; e < HB_SLOTS * 48; e += 128) {
+      const int sl = e / 48, j = e - sl * 48;
+      const long long slot = s0 + sl;
+      float v = 0.f;
+      if (slot < n_slots && j < nk) {
+        float d[3], tm;
+        if (src.mode == SRC_EXPLICIT) {
+          d[0] = src.dirs[3 * slot]; d[1] = src.dirs[3 * slot + 1]; d[2] = src.dirs[3 * slot + 2];
+          tm = src.times ? src.times[slot * src.time_stride] : 0.f;
+        } else {
+          const long long ray = src.hit ? (long long)src.hit[slot] : slot;
+          const float* rp = src.rays + ray * src.ray_stride;
+          d[0] = rp[3]; d[1] = rp[4]; d[2] = rp[5];
+          tm = rp[6 + src.layer];
+        }
+        if (j < PE_DIR) {
+          if (j < 3) v = d[j];
+          else {
+            const int r = j - 3, f = r / 6, m = r - 6 * f;        // [sin xyz | cos xyz] per frequency
+            const float a = d[m % 3] * (float)(1 << f);
+            v = (m < 3) ? sinf(a) : cosf(a);
+          }
+        } else {
+          const int r = j - PE_DIR;
+          if (r == 0) v = tm;
+          else {
+            const int f = (r - 1) >> 1;
+            const float a = tm * (float)(1 << f);
+            v = ((r - 1) & 1) ? cosf(a) : sinf(a);
+          }
+        }
+        v = fmaxf(v, 0.f);
+      }
+      s_enc[sl][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sl = 0; sl < HB_SLOTS; ++sl) {
+      const long long slot = s0 + sl;
+      if (slot >= n_slots) break;
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < 48; ++k) acc = fmaf(w[k], s_enc[sl][k], acc);
+      cbuf[slot * 128 + tid] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// self-test: 128 x N x 64 fp16 UMMA (N = 256) through exactly the descriptors / swizzles / bulk copy / TMEM load used above
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bstages,
                                                               float* __restrict__ D) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar = sbase + 2 * BLOCK_BYTES, bar2 = bar + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * BLOCK_BYTES + 16);
+  const uint32_t bar = sbase + ABLOCK + 2 * STAGE_BYTES, bar2 = bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ABLOCK + 2 * STAGE_BYTES + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((sbase & 1023u) != 0) __trap();
   if (tid == 0) {
@@ -622,81 +711,95 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* __r
     mbar_init(bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
-  // A: row `tid`, 64 columns, written with the epilogue's element mapping
-  for (int c = 0; c < 64; ++c) *reinterpret_cast<__half*>(smem + sw128_offset(tid, c)) = A[tid * 64 + c];
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  // A: row `tid`, 64 columns, written with the epilogue's store path (hi only)
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    float v[32];
+    for (int i = 0; i < 32; ++i) v[i] = A[tid * 64 + c0 + i];
+    store_row_split<32>(smem, 0, tid, c0, v, false);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) {
-    // B arrives through the same bulk-copy path as the weight ring
-    mbar_expect_tx(bar2, BLOCK_BYTES);
-    bulk_g2s(sbase + BLOCK_BYTES, Bblk, BLOCK_BYTES, bar2);
+    mbar_expect_tx(bar2, 2 * STAGE_BYTES);                       // two 32-wide k sub-chunks
+    bulk_g2s(sbase + ABLOCK, Bstages, 2 * STAGE_BYTES, bar2);
     mbar_wait(bar2, 0);
     tc_fence_after();
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      umma_f16(tmem_base, make_desc(sbase + ks * 32), make_desc(sbase + BLOCK_BYTES + ks * 32), IDESC_N128, ks ? 1u : 0u);
+    for (int sub = 0; sub < 2; ++sub)
+      for (int ks = 0; ks < 2; ++ks)
+        umma_f16(tmem_base, make_desc_sw128(sbase + sub * 64 + ks * 32),
+                 make_desc_sw64(sbase + ABLOCK + sub * STAGE_BYTES + ks * 32), idesc_n(256), (sub | ks) ? 1u : 0u);
     umma_commit(bar);
   }
   mbar_wait(bar, 0);
   tc_fence_after();
-  for (int j = 0; j < 4; ++j) {
-    float acc[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, acc);
+  for (int j = 0; j < 8; ++j) {
+    uint32_t acc[32];
+    tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, acc);
+    tmem_ld_wait(acc);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) D[(warp * 32 + lane) * 128 + j * 32 + i] = acc[i];
+    for (int i = 0; i < 32; ++i) D[(warp * 32 + lane) * 256 + j * 32 + i] = __uint_as_float(acc[i]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // host: weight packing
 // ---------------------------------------------------------------------------------------------------------
-// Emit the hi and lo blocks of W[n0..n0+127][k0..k0+63] (W row-major (N,K), zero outside) in the SW128 image.
-void emit_block_pair(std::vector<uint8_t>& hi, std::vector<uint8_t>& lo, const float* W, int N, int K, int ldw, int n0,
-                     int k0, int kvalid0, int kvalid1) {
-  hi.assign(BLOCK_BYTES, 0);
-  lo.assign(BLOCK_BYTES, 0);
-  for (int r = 0; r < 128; ++r) {
-    const int n = n0 + r;
-    if (n >= N) continue;
-    for (int c = 0; c < 64; ++c) {
-      const int k = k0 + c;
-      if (k < kvalid0 || k >= kvalid1 || k >= K) continue;
-      const float w = W[(size_t)n * ldw + k];
-      const __half h = __float2half_rn(w);
-      const __half l = __float2half_rn(w - __half2float(h));
-      const uint32_t off = sw128_offset(r, c);
-      memcpy(hi.data() + off, &h, 2);
-      memcpy(lo.data() + off, &l, 2);
-    }
-  }
+// One layer of the stream.  W is (N, K_total) row-major.  A 64-wide k-chunk is described by the 64 source columns it
+// multiplies (-1 = zero padding), in the column order the device writes its A operand.
+struct LayerSpec { const float* W; int N, K_total; std::vector<std::vector<int>> chunks; };
+
+std::vector<int> iota_chunk(int k0, int kend) {
+  std::vector<int> c(64, -1);
+  for (int i = 0; i < 64 && k0 + i < kend; ++i) c[i] = k0 + i;
+  return c;
+}
+// encoding-buffer column -> reference PE column (see encode_row)
+std::vector<int> enc_perm_space(int base) {
+  std::vector<int> c(64, -1);
+  c[0] = base + 0; c[1] = base + 1;
+  for (int i = 0; i < 30; ++i) c[2 + i] = base + 3 + i;            // f0..f4
+  c[32] = base + 2;
+  for (int i = 0; i < 30; ++i) c[33 + i] = base + 33 + i;          // f5..f9
+  return c;
+}
+std::vector<std::vector<int>> enc_perm_motion() {
+  std::vector<int> c0(64, -1), c1(64, -1);
+  for (int i = 0; i < 44; ++i) c0[i] = i;
+  for (int i = 0; i < 40; ++i) c1[i] = 44 + i;
+  return {c0, c1};
 }
 
-struct LayerSpec { const float* W; int N, K_total; int act_k; int enc_k0, enc_k; };   // W (N, K_total) row-major
-
-int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vector<float>& aux) {
-  std::vector<uint8_t> stream, hi, lo;
+int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vector<float>& aux, size_t expect_bytes) {
+  std::vector<uint8_t> stream;
   for (const LayerSpec& L : layers) {
-    const int nh = (L.N + 127) / 128;
-    // k-chunks: act part (columns [0, act_k)) then enc part (columns [enc_k0, enc_k0 + enc_k)), each in 64-wide chunks
-    std::vector<std::pair<int, int>> chunks;      // (k0, kend)
-    for (int k = 0; k < L.act_k; k += 64) chunks.push_back({k, std::min(k + 64, L.act_k)});
-    for (int k = 0; k < L.enc_k; k += 64) chunks.push_back({L.enc_k0 + k, L.enc_k0 + std::min(k + 64, L.enc_k)});
-    for (auto& ch : chunks) {
-      std::vector<std::vector<uint8_t>> his(nh), los(nh);
-      for (int h = 0; h < nh; ++h) emit_block_pair(his[h], los[h], L.W, L.N, L.K_total, L.K_total, h * 128, ch.first, ch.first, ch.second);
-      for (int h = 0; h < nh; ++h) stream.insert(stream.end(), his[h].begin(), his[h].end());
-      for (int h = 0; h < nh; ++h) stream.insert(stream.end(), los[h].begin(), los[h].end());
-    }
+    const size_t stage = (size_t)L.N * 64;
+    for (const auto& ch : L.chunks)
+      for (int sub = 0; sub < 2; ++sub) {
+        std::vector<uint8_t> hi(stage, 0), lo(stage, 0);
+        for (int n = 0; n < L.N; ++n)
+          for (int c = 0; c < 32; ++c) {
+            const int k = ch[sub * 32 + c];
+            if (k < 0) continue;
+            const float w = L.W[(size_t)n * L.K_total + k];
+            const __half h = __float2half_rn(w);
+            const __half l = __float2half_rn(w - __half2float(h));
+            const uint32_t off = sw64_offset(n, c);
+            memcpy(hi.data() + off, &h, 2);
+            memcpy(lo.data() + off, &l, 2);
+          }
+        stream.insert(stream.end(), hi.begin(), hi.end());
+        stream.insert(stream.end(), lo.begin(), lo.end());
+      }
   }
+  if (stream.size() != expect_bytes) return STNERF_EINVAL;
   tc_free(net);
-  net.n_blocks = (int)(stream.size() / BLOCK_BYTES);
   net.blob_bytes = stream.size();
   STNERF_CUDA(cudaMalloc(&net.blob, stream.size()));
   STNERF_CUDA(cudaMemcpy(net.blob, stream.data(), stream.size(), cudaMemcpyHostToDevice));
@@ -710,7 +813,8 @@ int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vec
 void tc_free(TcNet& net) {
   if (net.blob) cudaFree(net.blob);
   if (net.aux) cudaFree(net.aux);
-  net.blob = nullptr; net.aux = nullptr; net.blob_bytes = 0; net.n_blocks = 0;
+  if (net.w_tail) cudaFree(net.w_tail);
+  net.blob = nullptr; net.aux = nullptr; net.w_tail = nullptr; net.blob_bytes = 0;
 }
 
 int tc_pack_spacenet(TcNet& net, const float* p, bool use_time) {
@@ -721,9 +825,9 @@ int tc_pack_spacenet(TcNet& net, const float* p, bool use_time) {
   for (int i = 0; i < 7; ++i) {
     LayerSpec L;
     L.W = p; L.N = HID; L.K_total = Ks[i];
-    if (i == 0) { L.act_k = 0; L.enc_k0 = 0; L.enc_k = PE_POS; }
-    else if (i == 4) { L.act_k = HID; L.enc_k0 = HID; L.enc_k = PE_POS; }     // cat[x, PE(pos)] (spacenet.py:137)
-    else { L.act_k = HID; L.enc_k0 = 0; L.enc_k = 0; }
+    if (i != 0) for (int k = 0; k < HID; k += 64) L.chunks.push_back(iota_chunk(k, HID));
+    if (i == 0) L.chunks.push_back(enc_perm_space(0));
+    if (i == 4) L.chunks.push_back(enc_perm_space(HID));            // cat[x, PE(pos)] (spacenet.py:137)
     layers.push_back(L);
     p += (size_t)HID * Ks[i];
     memcpy(aux.data() + AUX_BIAS + i * 256, p, HID * sizeof(float));
@@ -731,17 +835,24 @@ int tc_pack_spacenet(TcNet& net, const float* p, bool use_time) {
   }
   memcpy(aux.data() + AUX_WSIG, p, HID * sizeof(float)); p += HID;
   aux[AUX_BSIG] = *p++;
-  LayerSpec L;
-  L.W = p; L.N = HEAD; L.K_total = krgb; L.act_k = HID; L.enc_k0 = HID; L.enc_k = krgb - HID;   // cat[x, PE(dir), PE(t)]
+  LayerSpec L;                                                      // rgb_net.1: only the x part goes through the GEMM
+  L.W = p; L.N = HEAD; L.K_total = krgb;
+  for (int k = 0; k < HID; k += 64) L.chunks.push_back(iota_chunk(k, HID));
   layers.push_back(L);
+  // dir/time tail of rgb_net.1, transposed [48][128] fp32, for head_bias_kernel
+  std::vector<float> tail(48 * 128, 0.f);
+  for (int n = 0; n < HEAD; ++n)
+    for (int k = 0; k < krgb - HID; ++k) tail[(size_t)k * 128 + n] = p[(size_t)n * krgb + HID + k];
   p += (size_t)HEAD * krgb;
   memcpy(aux.data() + AUX_BIAS + 7 * 256, p, HEAD * sizeof(float)); p += HEAD;
   memcpy(aux.data() + AUX_WOUT, p, 3 * HEAD * sizeof(float)); p += 3 * HEAD;
   memcpy(aux.data() + AUX_BOUT, p, 3 * sizeof(float));
   net.use_time = use_time ? 1 : 0;
-  const int rc = pack_stream(net, layers, aux);
+  const int rc = pack_stream(net, layers, aux, stream_bytes_per_tile<NET_SPACE>());
   if (rc) return rc;
-  return net.n_blocks == blocks_per_tile<NET_SPACE>() ? STNERF_OK : STNERF_EINVAL;
+  STNERF_CUDA(cudaMalloc((void**)&net.w_tail, tail.size() * sizeof(float)));
+  STNERF_CUDA(cudaMemcpy(net.w_tail, tail.data(), tail.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return STNERF_OK;
 }
 
 int tc_pack_motionnet(TcNet& net, const float* p) {
@@ -751,8 +862,8 @@ int tc_pack_motionnet(TcNet& net, const float* p) {
     LayerSpec L;
     const int K = i == 0 ? PE_MOTION : HEAD;
     L.W = p; L.N = HEAD; L.K_total = K;
-    if (i == 0) { L.act_k = 0; L.enc_k0 = 0; L.enc_k = 128; }       // PE(84) zero-padded to two 64-wide chunks
-    else { L.act_k = HEAD; L.enc_k0 = 0; L.enc_k = 0; }
+    if (i == 0) L.chunks = enc_perm_motion();                       // PE(84) in two 64-wide chunks (zero padded)
+    else for (int k = 0; k < HEAD; k += 64) L.chunks.push_back(iota_chunk(k, HEAD));
     layers.push_back(L);
     p += (size_t)HEAD * K;
     memcpy(aux.data() + AUX_BIAS + i * 256, p, HEAD * sizeof(float));
@@ -760,44 +871,43 @@ int tc_pack_motionnet(TcNet& net, const float* p) {
   }
   memcpy(aux.data() + AUX_WOUT, p, 3 * HEAD * sizeof(float)); p += 3 * HEAD;
   memcpy(aux.data() + AUX_BOUT, p, 3 * sizeof(float));
-  const int rc = pack_stream(net, layers, aux);
-  if (rc) return rc;
-  return net.n_blocks == blocks_per_tile<NET_MOTION>() ? STNERF_OK : STNERF_EINVAL;
+  return pack_stream(net, layers, aux, stream_bytes_per_tile<NET_MOTION>());
 }
 
-// D = A * B^T for random fp16 A (128x64), B (128x64) through the tensor-core path; returns max |D - reference|.
+// D = A * B^T for random A (128x64, rounded to fp16), B (256x64) through the tensor-core path; max |D - reference|.
 int tc_selftest(float* max_err_host) {
-  std::vector<__half> A(128 * 64), B(128 * 64);
-  std::vector<float> Af(128 * 64), Bf(128 * 64);
+  std::vector<float> Af(128 * 64), Bf(256 * 64);
   uint32_t s = 12345u;
   auto rnd = [&s]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
-  for (int i = 0; i < 128 * 64; ++i) {
-    A[i] = __float2half_rn(rnd()); Af[i] = __half2float(A[i]);
-    B[i] = __float2half_rn(rnd()); Bf[i] = __half2float(B[i]);
-  }
-  std::vector<uint8_t> blk(BLOCK_BYTES, 0);
-  for (int r = 0; r < 128; ++r)
-    for (int c = 0; c < 64; ++c) memcpy(blk.data() + sw128_offset(r, c), &B[r * 64 + c], 2);
-  __half* dA = nullptr; uint8_t* dB = nullptr; float* dD = nullptr;
-  STNERF_CUDA(cudaMalloc((void**)&dA, A.size() * 2));
-  STNERF_CUDA(cudaMalloc((void**)&dB, BLOCK_BYTES));
-  STNERF_CUDA(cudaMalloc((void**)&dD, 128 * 128 * 4));
-  STNERF_CUDA(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice));
-  STNERF_CUDA(cudaMemcpy(dB, blk.data(), BLOCK_BYTES, cudaMemcpyHostToDevice));
-  const int smem = 2 * BLOCK_BYTES + 64;
+  for (auto& v : Af) v = __half2float(__float2half_rn(rnd()));
+  for (auto& v : Bf) v = __half2float(__float2half_rn(rnd()));
+  std::vector<uint8_t> stages(2 * STAGE_BYTES, 0);
+  for (int sub = 0; sub < 2; ++sub)
+    for (int n = 0; n < 256; ++n)
+      for (int c = 0; c < 32; ++c) {
+        const __half h = __float2half_rn(Bf[n * 64 + sub * 32 + c]);
+        memcpy(stages.data() + sub * STAGE_BYTES + sw64_offset(n, c), &h, 2);
+      }
+  float *dA = nullptr, *dD = nullptr; uint8_t* dB = nullptr;
+  STNERF_CUDA(cudaMalloc((void**)&dA, Af.size() * 4));
+  STNERF_CUDA(cudaMalloc((void**)&dB, stages.size()));
+  STNERF_CUDA(cudaMalloc((void**)&dD, 128 * 256 * 4));
+  STNERF_CUDA(cudaMemcpy(dA, Af.data(), Af.size() * 4, cudaMemcpyHostToDevice));
+  STNERF_CUDA(cudaMemcpy(dB, stages.data(), stages.size(), cudaMemcpyHostToDevice));
+  const int smem = ABLOCK + 2 * STAGE_BYTES + 64;
   STNERF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD);
   STNERF_LAUNCH_CHECK();
   STNERF_CUDA(cudaDeviceSynchronize());
-  std::vector<float> D(128 * 128);
+  std::vector<float> D(128 * 256);
   STNERF_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
   float worst = 0.f;
   for (int m = 0; m < 128; ++m)
-    for (int n = 0; n < 128; ++n) {
+    for (int n = 0; n < 256; ++n) {
       double ref = 0;
       for (int k = 0; k < 64; ++k) ref += (double)Af[m * 64 + k] * Bf[n * 64 + k];
-      worst = fmaxf(worst, fabsf((float)ref - D[m * 128 + n]));
+      worst = fmaxf(worst, fabsf((float)ref - D[m * 256 + n]));
     }
   *max_err_host = worst;
   return STNERF_OK;
@@ -806,23 +916,32 @@ int tc_selftest(float* max_err_host) {
 template <int NET>
 static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   static bool configured = false;
-  const int smem = SM_TOTAL;
   if (!configured) {
-    STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
-  mlp_tc_kernel<NET><<<num_sms, NTHREADS, smem, st>>>(P);
+  mlp_tc_kernel<NET><<<num_sms, NTHREADS, SM_TOTAL, st>>>(P);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
 }
 
-int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, int precision, float* raw, float* rgb_out,
-                       float* sigma_out, int num_sms, cudaStream_t st) {
-  if (!net.blob) return STNERF_ENOWEIGHTS;
+int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, int precision, float* cbuf, float* raw,
+                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st) {
+  if (!net.blob || !net.w_tail) return STNERF_ENOWEIGHTS;
+  if (!cbuf) return STNERF_EINVAL;
+  // per-slot bias of rgb_net.1 (dir/time part), then the fused MLP
+  PointSrc hs = src;
+  if (src.mode == SRC_EXPLICIT) hs.count = nullptr;
+  const long long slots_hint = src.count ? src.n_slots_cap : src.n_slots;
+  long long blocks = (slots_hint + HB_SLOTS - 1) / HB_SLOTS;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  head_bias_kernel<<<(int)blocks, 128, 0, st>>>(hs, net.w_tail, net.aux + AUX_BIAS + 7 * 256, net.use_time, cbuf);
+  STNERF_LAUNCH_CHECK();
   TcParams P;
   memset(&P, 0, sizeof(P));
-  P.src = src; P.wblocks = (const uint8_t*)net.blob; P.aux = net.aux;
-  P.exact = precision == STNERF_PREC_TC_3XF16; P.use_time = net.use_time;
+  P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux; P.cbuf = cbuf;
+  P.exact = precision == STNERF_PREC_TC_3XF16;
   P.raw = raw; P.rgb_out = rgb_out; P.sigma_out = sigma_out; P.lerp_force = 0;
   return launch_tc<NET_SPACE>(P, num_sms, st);
 }
@@ -832,7 +951,7 @@ int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW&
   if (!net.blob) return STNERF_ENOWEIGHTS;
   TcParams P;
   memset(&P, 0, sizeof(P));
-  P.src = src; P.wblocks = (const uint8_t*)net.blob; P.aux = net.aux;
+  P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux;
   P.exact = precision == STNERF_PREC_TC_3XF16;
   P.xyz_out = xyz_out; P.flow_out = flow_out; P.lerp_flag = lerp_flag_dev; P.lerp_force = lerp_force;
   return launch_tc<NET_MOTION>(P, num_sms, st);

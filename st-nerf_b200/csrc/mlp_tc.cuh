@@ -9,7 +9,7 @@ struct TcNet {
   void* blob = nullptr;        // device: fp16 hi/lo weight blocks in the 128B-swizzled K-major SMEM image
   size_t blob_bytes = 0;
   float* aux = nullptr;        // device: fp32 biases / head weights
-  int n_blocks = 0;
+  float* w_tail = nullptr;     // device: SpaceNet rgb_net.1 columns 256.. transposed [48][128] fp32 (head_bias_kernel)
   int use_time = 0;
 };
 
@@ -17,7 +17,7 @@ int tc_pack_spacenet(TcNet& net, const float* blob_host, bool use_time);
 int tc_pack_motionnet(TcNet& net, const float* blob_host);
 void tc_free(TcNet& net);
 int tc_selftest(float* max_err_host);   // one 128x128x64 UMMA vs a host reference
-int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* raw,
+int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* cbuf, float* raw,
                        float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st);
 int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW& w32, int precision,
                         const int* lerp_flag_dev, int lerp_force, float* xyz_out, float* flow_out, int num_sms,
