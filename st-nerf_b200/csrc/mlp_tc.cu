@@ -76,11 +76,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) {
-      printf("stnerf mlp_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
+    if (spin > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -354,6 +350,58 @@ __device__ __forceinline__ void encode_row(uint8_t* smem, const Pt& pt, int row,
   else encode_row_half<NET, 1>(smem, pt, row, exact, lerp);
 }
 
+// One 64-column chunk of a hidden layer's epilogue for this thread's row: 32 accumulator columns (column half hh)
+// -> bias + ReLU (+ optional fp32 dot with a head weight vector) -> fp16 hi/lo -> 16-byte stores -> release to the MMA warp.
+template <bool SIGMA>
+__device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, int row, const float* __restrict__ bias,
+                                                  const float* __restrict__ wdot, uint8_t* blk, int lo_stride, bool exact,
+                                                  int lane, uint32_t ready_bar, float dot) {
+  uint32_t acc[32];
+  const int col0 = j * 64 + hh * 32;
+  tmem_ld32_issue(dcol + (uint32_t)col0, acc);
+  float4 bv[8], wv[8];
+  {
+    const float4* bp = reinterpret_cast<const float4*>(bias + col0);      // L1-resident; overlaps the TMEM load
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+    if (SIGMA) {
+      const float4* wp = reinterpret_cast<const float4*>(wdot + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wv[i] = __ldg(wp + i);
+    }
+  }
+  tmem_ld_wait(acc);
+#pragma unroll
+  for (int gq = 0; gq < 4; ++gq) {                     // 8 columns -> one 16-byte chunk
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = gq * 8 + e * 2;
+      const float4 bb = bv[c >> 2];
+      const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
+      const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
+      const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
+      if (SIGMA) {
+        const float4 ww = wv[c >> 2];
+        dot = fmaf(v0, (c & 2) ? ww.z : ww.x, dot);
+        dot = fmaf(v1, (c & 2) ? ww.w : ww.y, dot);
+      }
+      hp[e] = pack_f16x2(v0, v1);
+      if (exact) {
+        const float2 hf = unpack_f16x2(hp[e]);
+        lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
+      }
+    }
+    const uint32_t off = sw128_offset(row, hh * 32 + gq * 8);
+    *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    if (exact) *reinterpret_cast<uint4*>(blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(ready_bar);
+  return dot;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -495,57 +543,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
         const float* bias = bias_all + l * 256;
         const uint32_t dcol = lane_taddr + b * 256;
         if (!last) {
-          const bool sigma_layer = (NET == NET_SPACE && l == 6);
-          // bias of the first chunk is fetched before the accumulator wait
-          float4 bv[8];
-          {
-            const float4* bp = reinterpret_cast<const float4*>(bias + hh * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
-          }
           mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
           tc_fence_after();
-          for (int j = 0; j < width / 64; ++j) {                 // 64-column chunk j -> ACT k-chunk j
-            uint32_t acc[32];
-            const int col0 = j * 64 + hh * 32;
-            tmem_ld32_issue(dcol + (uint32_t)col0, acc);
-            float4 bn[8];
-            if (j + 1 < width / 64) {                            // next chunk's bias while the TMEM load is in flight
-              const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 64);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) bn[i] = __ldg(bp + i);
-            }
-            tmem_ld_wait(acc);
-            uint8_t* blk = smem + S::act_base + j * ABLOCK;
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {                     // 8 columns -> one 16-byte chunk
-              uint32_t hp[4], lp[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = gq * 8 + e * 2;
-                const float4 bb = bv[c >> 2];
-                const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
-                const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
-                const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
-                if (sigma_layer) {
-                  sig_dot = fmaf(v0, __ldg(P.aux + AUX_WSIG + col0 + c), sig_dot);
-                  sig_dot = fmaf(v1, __ldg(P.aux + AUX_WSIG + col0 + c + 1), sig_dot);
-                }
-                hp[e] = pack_f16x2(v0, v1);
-                if (exact) {
-                  const float2 hf = unpack_f16x2(hp[e]);
-                  lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
-                }
-              }
-              const uint32_t off = sw128_offset(row, hh * 32 + gq * 8);
-              *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-              if (exact) *reinterpret_cast<uint4*>(blk + S::LO_STRIDE + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_AREADY + j));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bv[i] = bn[i];
+          const int nchunk = width / 64;
+          if (NET == NET_SPACE && l == 6) {
+            for (int j = 0; j < nchunk; ++j)
+              sig_dot = epi_hidden_chunk<true>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
+                                               S::LO_STRIDE, exact, lane, BAR(BAR_AREADY + j), sig_dot);
+          } else {
+            for (int j = 0; j < nchunk; ++j)
+              epi_hidden_chunk<false>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, exact,
+                                      lane, BAR(BAR_AREADY + j), 0.f);
           }
           tc_fence_before();
           __syncwarp();
