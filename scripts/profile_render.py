@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Small driver for ncu: renders `--rays` rays of view 0 of the bench workload once (plus one warm-up call)."""
-import argparse, os, sys
+"""Small driver for ncu and A/B timing: renders `--rays` rays of view 0 of the bench workload `--calls` times and prints
+the per-kernel-class CUDA-event times (stnerf_profile_*)."""
+import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
     sys.path.insert(0, p)
@@ -14,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=65536)
 ap.add_argument("--precision", default="exact")
 ap.add_argument("--calls", type=int, default=2)
+ap.add_argument("--warm", type=int, default=1)
 a = ap.parse_args()
 sd, _ = B.load_weights()
 bkgd, frames, cams = B.scene_setup()
@@ -25,7 +27,13 @@ nat.set_scene(m._resolve_scene(torch.tensor(B.FRAME_IDS), 0.0, 0.0))
 K, T = cams[0]
 rows = (a.rays + B.W - 1) // B.W
 rays = ops.generate_rays(K, T, B.H, B.W, frame_ids=B.FRAME_IDS, row0=(B.H - rows) // 2, n_rows=rows)[:a.rays].contiguous()
-for i in range(a.calls):
+for i in range(a.warm):
     nat.render(rays, B.N1, B.N2, seed=i + 1)
 torch.cuda.synchronize()
-print("rendered", rays.shape[0], "rays x", a.calls)
+nat.profile_begin()
+for i in range(a.calls):
+    nat.render(rays, B.N1, B.N2, seed=100 + i)
+prof = nat.profile_end()
+print(json.dumps({"lib": os.environ.get("STNERF_B200_LIB", "default"), "rays": rays.shape[0], "calls": a.calls,
+                  "ms_per_call": {k: round(v["ms"] / a.calls, 3) for k, v in prof.items()},
+                  "points": {k: v["points"] / a.calls for k, v in prof.items()}}))

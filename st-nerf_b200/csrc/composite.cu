@@ -58,6 +58,24 @@ __device__ __forceinline__ void warp_bitonic_sort(T* a, int P, int lane) {
   }
 }
 
+// first index with a[idx] >= key / > key in an ascending shared-memory array
+__device__ __forceinline__ int lower_bound_s(const float* a, int n, float key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_s(const float* a, int n, float key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// warp-uniform: is a[0..n) non-decreasing?
+__device__ __forceinline__ bool warp_is_ascending(const float* a, int n, int lane) {
+  bool ok = true;
+  for (int k = lane; k + 1 < n; k += 32) ok = ok && (a[k] <= a[k + 1]);
+  return __all_sync(FULL, ok);
+}
+
 // gen_weight + VolumeRenderer.forward over `count` samples addressed through `at(j)` (position in the
 // per-warp arrays).  All lanes return the reduced color/depth/acc.  If w_out != null, w_out[j] = weight.
 template <typename At>
@@ -159,6 +177,7 @@ static PassSmem pass_layout(int l, int S, int n2) {
   L.off_sort = (L.off_sort + 1) & ~1;       // 8-byte aligned for the uint64 keys
   int sf = 2 * next_pow2(tot);
   if (n2 > 0 && next_pow2(S + n2) > sf) sf = next_pow2(S + n2);
+  if (n2 > 0 && S + next_pow2(n2) > sf) sf = S + next_pow2(n2);
   L.sort_floats = sf;
   L.per_warp_floats = (L.off_sort + sf + 3) & ~3;
   return L;
@@ -187,6 +206,7 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
   for (long long r = (long long)blockIdx.x * wpb + warp; r < a.n; r += (long long)gridDim.x * wpb) {
     const long long rg = a.ray_base + r;
     int n_m = 0;                                  // entries gathered for the merged composite
+    bool all_asc = true;                          // every gathered list is non-decreasing (always true for fine passes)
     for (int i = 0; i < n_layers; ++i) {
       float* oimg = a.out + (size_t)(1 + i) * plane;
       const bool hit = (i == 0) || (a.mask[i * a.mask_layer_stride + r] != 0);
@@ -229,6 +249,8 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
         s_b[off + k] = sigmoidf_ref(cb);
       }
       __syncwarp();
+      const bool asc = warp_is_ascending(s_t + off, S, lane);
+      all_asc = all_asc && asc;
       float o5[5];
       const bool want_w = (!fine) && n2 > 0;
       composite_run(S, [off](int j) { return off + j; }, s_t, s_sig, s_r, s_g, s_b, boarder, 0.f, false,
@@ -246,27 +268,65 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
                          return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, (uint64_t)rg, (uint32_t)j);
                        },
                        s_cdf, s_sortf + S, lane);
-        const int S2 = S + n2, P = next_pow2(S2);
-        for (int k = lane; k < S; k += 32) s_sortf[k] = s_t[off + k];
-        for (int k = S2 + lane; k < P; k += 32) s_sortf[k] = CUDART_INF_F;
-        __syncwarp();
-        warp_bitonic_sort(s_sortf, P, lane);                                    // torch.sort(cat(t, z)) :462
+        const int S2 = S + n2;
         float* tf = a.t_fine + i * a.tf_layer_stride + r * S2;
-        for (int k = lane; k < S2; k += 32) tf[k] = s_sortf[k];
+        if (asc) {
+          // torch.sort(cat(t, z)) (:462) = sort the n2 new depths, then rank-merge with the ascending coarse depths
+          float* zs = s_sortf + S;
+          const int P2 = next_pow2(n2);
+          for (int k = n2 + lane; k < P2; k += 32) zs[k] = CUDART_INF_F;
+          __syncwarp();
+          warp_bitonic_sort(zs, P2, lane);
+          for (int k = lane; k < S; k += 32) {
+            const float v = s_t[off + k];
+            tf[k + lower_bound_s(zs, n2, v)] = v;
+          }
+          for (int k = lane; k < n2; k += 32) {
+            const float v = zs[k];
+            tf[k + upper_bound_s(s_t + off, S, v)] = v;
+          }
+        } else {
+          const int P = next_pow2(S2);
+          for (int k = lane; k < S; k += 32) s_sortf[k] = s_t[off + k];
+          for (int k = S2 + lane; k < P; k += 32) s_sortf[k] = CUDART_INF_F;
+          __syncwarp();
+          warp_bitonic_sort(s_sortf, P, lane);
+          for (int k = lane; k < S2; k += 32) tf[k] = s_sortf[k];
+        }
         __syncwarp();
       }
       n_m += S;
     }
     // ---- merged composite over every hit layer's samples, ordered by (t, cat index)  (:425-448 / :587-606)
     {
-      const int P = next_pow2(n_m);
-      for (int j = lane; j < P; j += 32)
-        s_sort64[j] = (j < n_m) ? (((unsigned long long)float_key(s_t[j]) << 32) | (unsigned)j) : ~0ull;
-      __syncwarp();
-      warp_bitonic_sort(s_sort64, P, lane);
       float o5[5];
-      composite_run(n_m, [s_sort64](int j) { return (int)(s_sort64[j] & 0xffffffffu); }, s_t, s_sig, s_r, s_g, s_b,
-                    boarder, near_p, fine, nullptr, lane, o5);
+      if (all_asc) {
+        // every list is sorted: the stable (t, cat index) order is a rank computation -- position of sample (h,k) =
+        // k + #(samples of earlier lists with t' <= t) + #(samples of later lists with t' < t)
+        uint16_t* order = reinterpret_cast<uint16_t*>(s_sortf);
+        const int n_lists = n_m / S;
+        for (int e = lane; e < n_m; e += 32) {
+          const int h = e / S;
+          const float key = s_t[e];
+          int pos = e - h * S;
+          for (int h2 = 0; h2 < n_lists; ++h2) {
+            if (h2 == h) continue;
+            pos += (h2 < h) ? upper_bound_s(s_t + h2 * S, S, key) : lower_bound_s(s_t + h2 * S, S, key);
+          }
+          order[pos] = (uint16_t)e;
+        }
+        __syncwarp();
+        composite_run(n_m, [order](int j) { return (int)order[j]; }, s_t, s_sig, s_r, s_g, s_b, boarder, near_p, fine,
+                      nullptr, lane, o5);
+      } else {
+        const int P = next_pow2(n_m);
+        for (int j = lane; j < P; j += 32)
+          s_sort64[j] = (j < n_m) ? (((unsigned long long)float_key(s_t[j]) << 32) | (unsigned)j) : ~0ull;
+        __syncwarp();
+        warp_bitonic_sort(s_sort64, P, lane);
+        composite_run(n_m, [s_sort64](int j) { return (int)(s_sort64[j] & 0xffffffffu); }, s_t, s_sig, s_r, s_g, s_b,
+                      boarder, near_p, fine, nullptr, lane, o5);
+      }
       float* oimg = a.out;
       if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
       if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
