@@ -113,6 +113,12 @@ int stnerf_render(stnerf_handle h, const float* rays, int64_t n_rays, int ray_st
                   int only_coarse, const float* jitter, const float* u, uint64_t seed,
                   float* out, uint8_t* ray_mask, void* stream);
 
+/* Keys of the in-kernel Philox stream: ray j of the following stnerf_render calls draws the uniforms of ray id
+ *   base + (j / width) * row_stride + (j % width)      (width = 0: id = base + j, the default).
+ * A caller that renders row-interleaved shards of an image (one process per GPU) sets base = first_row * W, width = W,
+ * row_stride = n_ranks * W so that every pixel gets the same draws as in an unsharded render of the same seed.         */
+int stnerf_set_ray_ids(stnerf_handle h, int64_t base, int32_t width, int64_t row_stride);
+
 /* Same call with HOST buffers (pinned or pageable): H2D of rays, render, D2H of out/ray_mask on `stream`,
  * returns after the stream has drained.  This is the e2e path bench.py times.                             */
 int stnerf_render_host(stnerf_handle h, const float* rays_host, int64_t n_rays, int ray_stride, int n1, int n2,

@@ -55,6 +55,7 @@ struct stnerf_ctx {
   uint8_t* h_mask = nullptr;
   size_t h_rays_bytes = 0, h_out_bytes = 0, h_mask_bytes = 0;
   int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
+  RayIdMap idmap{0, 0, 0};     // stnerf_set_ray_ids
   // profiling (stnerf_profile_begin / _end): CUDA-event pairs around every launch, on the launching stream
   struct ProfRec { int cls; cudaEvent_t a, b; double points; int count_slot; int S; };
   bool prof_on = false;
@@ -383,7 +384,7 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
     int chunk_slot = -1;
     {
       ProfScope ps(c, 2, (double)n, -1, 1, st);
-      rc = launch_sample(rch, n, ray_stride, c->dscene, l, n1, jitter ? jitter + c0 * n1 : nullptr, N * n1, seed, c0,
+      rc = launch_sample(rch, n, ray_stride, c->dscene, l, n1, jitter ? jitter + c0 * n1 : nullptr, N * n1, seed, c0, c->idmap,
                          c->t_coarse, R * c->cap_n1, mask, mask_ls, c->hit, R, c->counts, c->lerp_flags, st);
       if (rc) return rc;
     }
@@ -403,7 +404,7 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
     a.u = u ? u + c0 * n2 : nullptr; a.u_layer_stride = N * n2;
     a.t_fine = c->t_fine; a.tf_layer_stride = R * c->cap_s2;
     a.out = out; a.n_total = N; a.ray_base = c0; a.n = n;
-    a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed;
+    a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed; a.idmap = c->idmap;
     {
       ProfScope ps(c, 3, (double)n, -1, 1, st);
       rc = launch_composite_pass(a, c->dscene, l, st);
@@ -451,6 +452,12 @@ int stnerf_render_host(stnerf_handle c, const float* rays_host, int64_t n_rays, 
   STNERF_CUDA(cudaMemcpyAsync(out_host, c->h_out, ob_used, cudaMemcpyDeviceToHost, st));
   if (ray_mask_host) STNERF_CUDA(cudaMemcpyAsync(ray_mask_host, c->h_mask, mb, cudaMemcpyDeviceToHost, st));
   STNERF_CUDA(cudaStreamSynchronize(st));
+  return STNERF_OK;
+}
+
+int stnerf_set_ray_ids(stnerf_handle c, int64_t base, int32_t width, int64_t row_stride) {
+  if (!c || width < 0) return STNERF_EINVAL;
+  c->idmap.base = base; c->idmap.width = width; c->idmap.row_stride = row_stride;
   return STNERF_OK;
 }
 

@@ -91,6 +91,17 @@ __device__ __forceinline__ long long src_num_points(const PointSrc& s) {
   return slots * (long long)s.S;
 }
 
+// Maps a ray's index within a call to the id that keys the Philox stream (identity by default).  A caller that renders
+// an image in row-interleaved shards sets (base, width, row_stride) so every pixel draws the same uniforms as in an
+// unsharded render:  id = base + (j / width) * row_stride + (j % width).
+struct RayIdMap {
+  long long base, row_stride;
+  int width;
+  __host__ __device__ unsigned long long operator()(long long j) const {
+    return width > 0 ? (unsigned long long)(base + (j / width) * row_stride + (j % width)) : (unsigned long long)(base + j);
+  }
+};
+
 // Scene constants as the kernels see them.
 struct DevScene {
   float bmin[STNERF_MAX_LAYERS][3];
@@ -133,7 +144,7 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t stream, 
 int launch_raygen(const float* Kinv, const float* T, int H, int W, int row0, int row_step, int n_rows,
                   const float* fids, int n_fids, float* rays, int ray_stride, cudaStream_t st);
 int launch_sample(const float* rays, long long n, int ray_stride, const DevScene& scene, int n_layers, int n1,
-                  const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base,
+                  const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base, RayIdMap idmap,
                   float* t_coarse, long long t_layer_stride, uint8_t* mask, long long mask_layer_stride,
                   int* hit, long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st);
 int launch_intersect_sample(const float* rays, long long n, int ray_stride, const float* bmin, const float* bmax,
@@ -159,6 +170,7 @@ struct CompositeArgs {
   long long n;             // rays in this chunk
   int S, n2, fine;
   uint64_t seed;
+  RayIdMap idmap;
 };
 int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_layers, cudaStream_t st);
 int launch_composite_simple(const float* t, const float* rgb, const float* sigma, long long n, int S, float boarder,

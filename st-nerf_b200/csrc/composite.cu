@@ -263,9 +263,10 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
         // hierarchical resampling of this layer (layered_rfrender.py:459-463)
         const float* up = a.u ? a.u + i * a.u_layer_stride + r * n2 : nullptr;
         const uint64_t seed = a.seed;
+        const unsigned long long gid = a.idmap(rg);
         sample_pdf_ray(s_t + off, s_w, S, n2,
-                       [up, seed, i, rg](int j) {
-                         return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, (uint64_t)rg, (uint32_t)j);
+                       [up, seed, i, gid](int j) {
+                         return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, gid, (uint32_t)j);
                        },
                        s_cdf, s_sortf + S, lane);
         const int S2 = S + n2;

@@ -54,7 +54,7 @@ constexpr int SAMPLE_BLOCK = 256;
 __global__ void __launch_bounds__(SAMPLE_BLOCK)
 sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const DevScene scene,
               int n_layers, int n1, const float* __restrict__ jitter, long long jitter_layer_stride, uint64_t seed,
-              long long ray_base, float* __restrict__ t_out, long long t_layer_stride, uint8_t* __restrict__ mask,
+              long long ray_base, RayIdMap idmap, float* __restrict__ t_out, long long t_layer_stride, uint8_t* __restrict__ mask,
               long long mask_layer_stride, int* __restrict__ hit, long long hit_layer_stride, int* __restrict__ counts,
               int* __restrict__ lerp_flags) {
   __shared__ float s_start[STNERF_MAX_LAYERS][SAMPLE_BLOCK];
@@ -119,7 +119,7 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
     const float* jl = jitter ? jitter + i * jitter_layer_stride + ray0 * n1 : nullptr;
     for (int idx = tid; idx < total; idx += SAMPLE_BLOCK) {
       const int rr = idx / n1, k = idx - rr * n1;
-      const float uu = jl ? jl[idx] : philox_uniform(seed, (uint32_t)i, (uint64_t)(ray_base + ray0 + rr), (uint32_t)k);
+      const float uu = jl ? jl[idx] : philox_uniform(seed, (uint32_t)i, idmap(ray_base + ray0 + rr), (uint32_t)k);
       const float a = (float)k + uu;
       tl[idx] = a * s_width[i][rr] + s_start[i][rr];
     }
@@ -127,13 +127,13 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
 }
 
 int launch_sample(const float* rays, long long n, int ray_stride, const DevScene& scene, int n_layers, int n1,
-                  const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base,
+                  const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base, RayIdMap idmap,
                   float* t_coarse, long long t_layer_stride, uint8_t* mask, long long mask_layer_stride, int* hit,
                   long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st) {
   if (n <= 0) return STNERF_OK;
   const int grid = (int)((n + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK);
   sample_kernel<<<grid, SAMPLE_BLOCK, 0, st>>>(rays, n, ray_stride, scene, n_layers, n1, jitter,
-                                               jitter_layer_stride, seed, ray_base, t_coarse, t_layer_stride, mask,
+                                               jitter_layer_stride, seed, ray_base, idmap, t_coarse, t_layer_stride, mask,
                                                mask_layer_stride, hit, hit_layer_stride, counts, lerp_flags);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;

@@ -67,12 +67,19 @@ class ShardedViewRenderer:
             rays = torch.cat([rays, pad], 0)
         return rays.contiguous()
 
-    def render(self, rays: torch.Tensor, seed: int = 0):
-        """Returns the assembled fine images (l+1, H, W, 5) = rgb(3), depth, acc on every rank."""
+    def render_local(self, rays: torch.Tensor, seed: int = 0):
+        """This rank's rows of the fine images: (l+1, rows_pad*W*5), pixel-interleaved rgb(3), depth, acc."""
+        # every pixel keeps the Philox stream it has in an unsharded render of the same seed
+        self.nat.set_ray_ids(self.row0 * self.W, self.W, self.step * self.W)
         out, _ = self.nat.render(rays, self.n1, self.n2, seed=seed, out=self.out, ray_mask=self.mask)
+        self.nat.set_ray_ids(0, 0, 0)
         n = self.rp * self.W
         fine = out[1]                                                     # (l+1, 5n): rgb(3n) | depth(n) | acc(n)
         local = torch.cat([fine[:, :3 * n].reshape(self.l + 1, n, 3), fine[:, 3 * n:4 * n].unsqueeze(-1),
                            fine[:, 4 * n:].unsqueeze(-1)], -1).reshape(self.l + 1, n * 5)
-        g = all_gather_planes(local, self.world)
+        return local
+
+    def render(self, rays: torch.Tensor, seed: int = 0):
+        """Returns the assembled fine images (l+1, H, W, 5) = rgb(3), depth, acc on every rank."""
+        g = all_gather_planes(self.render_local(rays, seed), self.world)
         return assemble_image(g, self.H, self.W, self.world)

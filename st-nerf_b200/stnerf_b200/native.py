@@ -129,6 +129,10 @@ class NativeRenderer:
                                          L.stream_ptr()), "stnerf_motionnet")
         return flow
 
+    def set_ray_ids(self, base: int = 0, width: int = 0, row_stride: int = 0):
+        """Philox keys of the rays of subsequent render calls (see include/stnerf.h: stnerf_set_ray_ids)."""
+        L.check(L.lib().stnerf_set_ray_ids(self._h, int(base), int(width), int(row_stride)), "stnerf_set_ray_ids")
+
     def profile_begin(self):
         L.check(L.lib().stnerf_profile_begin(self._h), "stnerf_profile_begin")
 
