@@ -235,7 +235,9 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI (H2D rays + D2H every plane inside the timed region) ----------
     e2e = None
-    rays_host = [r.cpu().pin_memory() for r in rays_dev[:2]]
+    # the same views as the first steps of the timed region (cost depends on how many rays hit the performers)
+    e2e_views = [(args.warmup + i) % VIEWS for i in range(max(1, args.e2e_steps))]
+    rays_host = [rays_dev[v].cpu().pin_memory() for v in e2e_views]
     out_host = torch.empty((2, 4, 5 * n_local), dtype=torch.float32).pin_memory()
     mask_host = torch.empty((3, n_local), dtype=torch.uint8).pin_memory()
     nat.render_host(rays_host[0], N1, N2, seed=99, out_host=out_host, mask_host=mask_host)   # warm staging buffers
@@ -244,7 +246,7 @@ def main():
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
-        nat.render_host(rays_host[i % 2], N1, N2, seed=100 + i, out_host=out_host, mask_host=mask_host)
+        nat.render_host(rays_host[i], N1, N2, seed=100 + i, out_host=out_host, mask_host=mask_host)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     te = torch.tensor([dt], device=dev)
@@ -274,12 +276,22 @@ def main():
     bk_pts = float(n_local) * (N1 + N1 + N2) * args.steps
     flops = bk_pts * FLOP_SPACE_BKGD + max(0.0, pts - bk_pts) * FLOP_SPACE_PERF
     ach = flops / (sp["ms"] * 1e-3) / 1e12 if sp["ms"] > 0 else 0.0
+    terms = 3 if args.precision == "exact" else 1
+    traffic, traffic_note = None, None
+    try:      # DRAM bytes per point of the same kernel from the committed `ncu --set full` capture, scaled to the mean launch
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_spacenet_traffic.json")))
+        traffic = cap["dram_bytes_per_point"] * pts / max(1, sp["launches"])
+        traffic_note = "dram__bytes_read+write per point (%.1f B, ncu --set full: %s) x mean points per launch" % (
+            cap["dram_bytes_per_point"], cap["kernel"])
+    except Exception:
+        pass
     roof = {"kernel": "spacenet MLP (%s)" % args.precision, "bound": "tensor", "achieved": ach, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "unit": "TFLOP/s", "frac": ach / peak_tf, "executed": ach * terms, "frac_executed": ach * terms / peak_tf,
             "peak_source": ("measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1400 (B200_PROFILING.md)"),
-            "traffic": None, "launches": sp["launches"], "avg_launch_ms": sp["ms"] / max(1, sp["launches"]),
+            "traffic": traffic, "traffic_note": traffic_note, "launches": sp["launches"], "avg_launch_ms": sp["ms"] / max(1, sp["launches"]),
             "share_of_step": sp["ms"] / ms_total,
-            "note": "algorithmic FLOPs (2*MAC/point x points evaluated); exact mode executes 3x these on the tensor pipe",
+            "note": "achieved/frac = algorithmic FLOPs (2*MAC/point x points evaluated); exact mode executes 3 fp16 MMAs per product "
+                    "(frac is capped at 1/3), executed/frac_executed = what the tensor pipe runs",
             "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "spacenet"}}
     # compositing kernel against the HBM roofline (algorithmic bytes: l*S*20 B in per ray-pass + outputs)
     cp = prof["composite"]

@@ -361,10 +361,11 @@ int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_l
 // Unit entry point a10: VolumeRenderer.forward on explicit (t, rgb, sigma) arrays.  Warp per ray, streaming:
 // 20 B/sample in, 4 B/sample out (weights) -- the HBM-roofline kernel of the compositing stage.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void composite_simple_kernel(const float* __restrict__ t, const float* __restrict__ rgb,
-                                        const float* __restrict__ sigma, long long n, int S, float boarder,
-                                        float* __restrict__ color, float* __restrict__ depth, float* __restrict__ acc,
-                                        float* __restrict__ w) {
+__global__ void __launch_bounds__(256) composite_simple_kernel(const float* __restrict__ t, const float* __restrict__ rgb,
+                                                              const float* __restrict__ sigma, long long n, int S, float boarder,
+                                                              float* __restrict__ color, float* __restrict__ depth,
+                                                              float* __restrict__ acc, float* __restrict__ w) {
+  constexpr int RB = 6;                      // rows of 32 samples whose loads are issued together (memory-level parallelism)
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -373,32 +374,52 @@ __global__ void composite_simple_kernel(const float* __restrict__ t, const float
     const float* sp = sigma + r * S;
     const float* cp = rgb + r * S * 3;
     float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
-    for (int base = 0; base < S; base += 32) {
-      const int j = base + lane;
-      const bool valid = j < S;
-      float f = 1.0f, alpha = 0.0f;
-      const float tj = valid ? tp[j] : 0.0f;
-      float tn = __shfl_down_sync(FULL, tj, 1);
-      if (lane == 31) tn = (j + 1 < S) ? tp[j + 1] : 0.0f;
-      if (valid) {
-        const float delta = (j == S - 1) ? boarder : (tn - tj);
-        const float e = expf(-fmaxf(sp[j], 0.0f) * delta);
-        alpha = 1.0f - e;
-        f = (1.0f - alpha) + 1e-10f;
+    for (int base = 0; base < S; base += 32 * RB) {
+      float tv[RB + 1], sv[RB], c0[RB], c1[RB], c2[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        const int j = base + q * 32 + lane;
+        const bool valid = j < S;
+        tv[q] = valid ? __ldg(tp + j) : 0.0f;
+        sv[q] = valid ? __ldg(sp + j) : 0.0f;
+        c0[q] = valid ? __ldg(cp + 3 * j) : 0.0f;
+        c1[q] = valid ? __ldg(cp + 3 * j + 1) : 0.0f;
+        c2[q] = valid ? __ldg(cp + 3 * j + 2) : 0.0f;
       }
-      const float incl = warp_incl_mul(f, lane);
-      float excl = __shfl_up_sync(FULL, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      const float T = carry * excl;
-      carry = carry * __shfl_sync(FULL, incl, 31);
-      if (valid) {
-        const float ww = alpha * T;
-        if (w) w[r * S + j] = ww;
-        cr += sigmoidf_ref(cp[3 * j]) * ww;
-        cg += sigmoidf_ref(cp[3 * j + 1]) * ww;
-        cb += sigmoidf_ref(cp[3 * j + 2]) * ww;
-        cd += ww * tj;
-        ca += ww;
+      {                                      // first depth of the next batch (delta of this batch's last sample)
+        const int jn = base + RB * 32;
+        tv[RB] = (lane == 0 && jn < S) ? __ldg(tp + jn) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        const int j = base + q * 32 + lane;
+        if (base + q * 32 >= S) break;       // warp-uniform
+        const bool valid = j < S;
+        const float tj = tv[q];
+        float tn = __shfl_down_sync(FULL, tj, 1);
+        const float tfirst_next = __shfl_sync(FULL, tv[q + 1], 0);
+        if (lane == 31) tn = tfirst_next;
+        float f = 1.0f, alpha = 0.0f;
+        if (valid) {
+          const float delta = (j == S - 1) ? boarder : (tn - tj);
+          const float e = expf(-fmaxf(sv[q], 0.0f) * delta);
+          alpha = 1.0f - e;
+          f = (1.0f - alpha) + 1e-10f;
+        }
+        const float incl = warp_incl_mul(f, lane);
+        float excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float T = carry * excl;
+        carry = carry * __shfl_sync(FULL, incl, 31);
+        if (valid) {
+          const float ww = alpha * T;
+          if (w) w[r * S + j] = ww;
+          cr += sigmoidf_ref(c0[q]) * ww;
+          cg += sigmoidf_ref(c1[q]) * ww;
+          cb += sigmoidf_ref(c2[q]) * ww;
+          cd += ww * tj;
+          ca += ww;
+        }
       }
     }
     cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); cd = warp_sum(cd); ca = warp_sum(ca);
@@ -415,7 +436,7 @@ int launch_composite_simple(const float* t, const float* rgb, const float* sigma
   if (n <= 0) return STNERF_OK;
   const int block = 256;
   long long blocks = (n * 32 + block - 1) / block;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   composite_simple_kernel<<<(int)blocks, block, 0, st>>>(t, rgb, sigma, n, S, boarder, color, depth, acc, w);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
