@@ -1,0 +1,122 @@
+"""GPU edge cases of the hot path, checked against the CPU oracle on the same seeded inputs (the oracle itself is pinned
+to the reference by tests/test_oracle_golden.py): maximum layer count, 64+192 samples, tiny sample counts, two rays,
+every performer hidden, padded ray rows, bad arguments."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle import stnerf_oracle as O
+from tests_support import make_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(L, n1, n2, n_rays, seed, hidden=(), thr=(0.5, 0.1), near=0.0, precision="exact", space_time=True,
+              extra_cols=0, frame_ids=None, keep=None):
+    import modeling
+    case = dict(weights="synthetic", seed=seed, L=L, space_time=space_time, n1=n1, n2=n2,
+                frame_ids=frame_ids or ([0] + [10 + i for i in range(L)]), thr=thr, n_rays=n_rays, ray_seed=seed,
+                hidden=list(hidden), near=near)
+    sd = C.state_dict_for(case)
+    rays = C.rays_for(case)
+    jit, u = C.uniforms_for(case)
+    if keep is not None:                            # render only the first `keep` rays of the generated set
+        rays, jit, u, n_rays = rays[:keep].contiguous(), jit[:, :keep].contiguous(), u[:, :keep].contiguous(), keep
+    nets = O.split_state_dict(sd, L)
+    want = O.render(nets, C.scene_for(case), rays, n1, n2, jit, u, density_threshold=thr[0], bkgd_density_threshold=thr[1])
+    want = C.flatten_outputs(want["fine_mixed"], want["coarse_mixed"], want["fine_layer"], want["coarse_layer"], want["ray_mask"])
+    model = modeling.build_layered_model(make_cfg(L, n1, n2, space_time, precision))
+    model.load_state_dict(sd)
+    bkgd, frames = C.boxes_for(case)
+    model.set_bkgd_bbox(bkgd); model.set_bboxes(frames); model.near = near
+    for i in hidden:
+        model.hide_layer(i)
+    dev = torch.device("cuda", 0)
+    r = rays.to(dev)
+    if extra_cols:       # rays with more columns than 6+l are not a reference layout; exercise the C-ABI stride instead
+        pad = torch.full((r.shape[0], r.shape[1] + extra_cols), 7.0, device=dev)
+        pad[:, :r.shape[1]] = r
+        r = pad[:, :r.shape[1]]                     # non-contiguous view with a wider row stride
+        assert r.stride(0) == rays.shape[1] + extra_cols
+        nat = model._ensure_native(dev)
+        nat.set_scene(model._resolve_scene(rays[0, 6:], thr[0], thr[1]))
+        from stnerf_b200 import _lib as Lb, split_planes
+        out = torch.empty((2, L + 2, 5 * n_rays), device=dev)
+        mask = torch.empty((L + 1, n_rays), dtype=torch.uint8, device=dev)
+        jd, ud = jit.to(dev), u.to(dev)             # keep the device copies alive across the asynchronous call
+        Lb.check(Lb.lib().stnerf_render(nat._h, Lb.ptr(r), n_rays, r.stride(0), n1, n2, 0, Lb.ptr(jd),
+                                        Lb.ptr(ud), 1, Lb.ptr(out), Lb.ptr(mask), Lb.stream_ptr()), "render")
+        torch.cuda.synchronize()
+        fm, cm, fl, cl = split_planes(out, L + 1)
+        got = C.flatten_outputs(fm, cm, fl, cl, [mask[i].bool() for i in range(L + 1)])
+    else:
+        model.inject_uniforms(jit.to(dev), u.to(dev))
+        with torch.no_grad():
+            got = C.flatten_outputs(*model(r, None, None, density_threshold=thr[0], bkgd_density_threshold=thr[1]))
+    torch.cuda.synchronize()
+    return got, want
+
+
+def _assert_close(got, want, rgb_tol=1e-3):
+    for k in sorted(want):
+        if k.startswith("ray_mask"):
+            assert np.array_equal(got[k], want[k]), k
+        elif k.endswith("rgb") or k.endswith("acc"):
+            err = np.abs(got[k].astype(np.float64) - want[k]).max()
+            assert err <= rgb_tol, "%s %.3e" % (k, err)
+        else:
+            assert (np.abs(got[k] - want[k]) <= 2e-2 + 2e-3 * np.abs(want[k])).all(), k
+
+
+def test_six_performers_64_192():
+    """BASELINE config #5 shape: 6 performer layers + background, 64 coarse + 192 fine samples (1792-sample merge)."""
+    got, want = _run_both(L=6, n1=64, n2=192, n_rays=70, seed=21, space_time=False)
+    _assert_close(got, want)
+    assert all(want["ray_mask.%d" % i].sum() > 0 for i in range(1, 7))
+
+
+def test_tiny_sample_counts():
+    got, want = _run_both(L=2, n1=8, n2=8, n_rays=96, seed=22)
+    _assert_close(got, want)
+
+
+def test_odd_sample_counts_fp32():
+    got, want = _run_both(L=1, n1=37, n2=53, n_rays=64, seed=23, precision="fp32")
+    _assert_close(got, want)
+
+
+def test_two_rays():
+    got, want = _run_both(L=2, n1=64, n2=128, n_rays=32, seed=24, keep=2)     # the smallest call the reference accepts
+    assert got["fine_mixed.rgb"].shape == (2, 3)
+    _assert_close(got, want)
+
+
+def test_all_performers_hidden():
+    got, want = _run_both(L=2, n1=64, n2=128, n_rays=96, seed=25, hidden=(1, 2))
+    _assert_close(got, want)
+    assert np.all(got["fine_layer.1.rgb"] == 0) and np.all(got["fine_layer.2.acc"] == 0)
+
+
+def test_wide_ray_stride_through_c_abi():
+    got, want = _run_both(L=2, n1=64, n2=128, n_rays=64, seed=26, extra_cols=3)
+    _assert_close(got, want)
+
+
+def test_c_abi_rejects_bad_arguments():
+    from stnerf_b200 import NativeRenderer, _lib as Lb
+    r = NativeRenderer(3, [False, True, True], "exact")
+    lib = Lb.lib()
+    rays = torch.zeros(16, 9, device="cuda")
+    out = torch.zeros(2, 4, 80, device="cuda")
+    args = lambda n1, n2, stride: (r._h, Lb.ptr(rays), 16, stride, n1, n2, 0, None, None, 0, Lb.ptr(out), None, Lb.stream_ptr())
+    assert lib.stnerf_render(*args(64, 128, 9)) == -1            # no scene set yet
+    r.set_scene(Lb.Scene())
+    assert lib.stnerf_render(*args(64, 128, 9)) == -4            # weights never loaded -> STNERF_ENOWEIGHTS
+    assert lib.stnerf_render(*args(2, 128, 9)) == -1             # n1 < 3
+    assert lib.stnerf_render(*args(64, 600, 9)) == -1            # n1 + n2 > STNERF_MAX_S
+    assert lib.stnerf_render(*args(64, 128, 8)) == -1            # ray row narrower than 6 + l
+    torch.cuda.synchronize()
+    r.close()
