@@ -37,16 +37,39 @@ for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"),
 H, W, VIEWS, N1, N2, LAYERS = 1080, 1920, 16, 64, 128, 2
 FRAME_IDS = [0.0, 10.0, 11.0]
 FLOP_SPACE_BKGD, FLOP_SPACE_PERF, FLOP_MOTION = 924672.0, 930048.0, 153344.0   # SURVEY 8(d), 2*MAC per point
+CKPT, SPACE_TIME, THR, NEAR = "taekwondo", True, (0.0, 0.0), 0.0                # demo/taekwondo_demo.py:44
+WORKLOAD_NAME = "taekwondo 2-layer 1080p, 16 views, 64+128 samples (BASELINE configs[1])"
+
+# The headline line is always configs[1] (default).  The other BASELINE configs can be timed for the record with --workload.
+WORKLOADS = {
+    "taekwondo2": None,
+    # configs[2]: walking nets replicated round-robin to 4 performers, demo/walking_demo.py:43-50 thresholds
+    "walking4": dict(H=1080, W=1920, VIEWS=16, N1=64, N2=128, LAYERS=4, CKPT="walking", SPACE_TIME=False, THR=(20.0, 0.8),
+                     NEAR=4.0, FLOP_SPACE_PERF=924672.0,
+                     WORKLOAD_NAME="walking 4-layer 1080p, 16 views, 64+128 samples (BASELINE configs[2])"),
+    # configs[4]: 6 performers, 4K, 32 views, 64+192
+    "walking6_4k": dict(H=2160, W=3840, VIEWS=32, N1=64, N2=192, LAYERS=6, CKPT="walking", SPACE_TIME=False,
+                        THR=(20.0, 0.8), NEAR=4.0, FLOP_SPACE_PERF=924672.0,
+                        WORKLOAD_NAME="walking 6-layer 4K, 32 views, 64+192 samples (BASELINE configs[4])"),
+}
+
+
+def select_workload(name):
+    w = WORKLOADS[name]
+    if w:
+        globals().update(w)
+        globals()["FRAME_IDS"] = [0.0] + [30.0 + i for i in range(w["LAYERS"])]
 
 
 def load_weights():
     import torch
     import cases as C
-    p = C.find_checkpoint("taekwondo")
+    p = C.find_checkpoint(CKPT)
     if p is not None:
-        return torch.load(p, map_location="cpu")["model"], "taekwondo checkpoint (oracle/_ref/ckpt)"
+        sd = C.replicate_layers(torch.load(p, map_location="cpu")["model"], LAYERS)
+        return sd, "%s checkpoint (oracle/_ref/ckpt)%s" % (CKPT, ", nets replicated round-robin to %d performers" % LAYERS if LAYERS > 2 else "")
     from oracle import stnerf_oracle as O          # seeded weights only; nothing is computed by the oracle here
-    return O.synthetic_state_dict(LAYERS, True, seed=7), "seeded random weights (checkpoint copy absent)"
+    return O.synthetic_state_dict(LAYERS, SPACE_TIME, seed=7), "seeded random weights (checkpoint copy absent)"
 
 
 def scene_setup():
@@ -101,7 +124,7 @@ def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
     nets = O.split_state_dict(sd, LAYERS)
     bkgd, frames, cams = scene_setup()
     sc = O.resolve_scene(frames, bkgd, FRAME_IDS, None, None)
-    sc.update(scale=None, shift=None, shown=[True] * 3, near=0.0, alpha=1.0, boarder=1e10)
+    sc.update(scale=None, shift=None, shown=[True] * (LAYERS + 1), near=NEAR, alpha=1.0, boarder=1e10)
     fid = torch.tensor(FRAME_IDS)[None]
     times = []
     gen = torch.Generator().manual_seed(1234)
@@ -113,12 +136,12 @@ def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
         full = O.generate_rays(K, T, H, W)
         idx = torch.arange(256) + (H // 2) * W + (W - 256) // 2
         rays = torch.cat([full[idx], fid.expand(256, -1)], 1)
-        jit, u = torch.rand((3, 256, N1), generator=gen), torch.rand((3, 256, N2), generator=gen)
+        jit, u = torch.rand((LAYERS + 1, 256, N1), generator=gen), torch.rand((LAYERS + 1, 256, N2), generator=gen)
         best = 0.0
         for _ in range(2):
             t0 = time.perf_counter()
             with torch.no_grad():
-                O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=0.0, bkgd_density_threshold=0.0)
+                O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
             best = max(best, 256 / (time.perf_counter() - t0))
         return best
 
@@ -134,11 +157,11 @@ def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
         per = max(1, sample_rays // 4)
         idx = torch.cat([torch.arange(per) + (H * (2 * q + 1) // 8) * W + (W - per) // 2 for q in range(4)])
         rays = torch.cat([full[idx], fid.expand(idx.numel(), -1)], 1)
-        jit = torch.rand((3, rays.shape[0], N1), generator=gen)
-        u = torch.rand((3, rays.shape[0], N2), generator=gen)
+        jit = torch.rand((LAYERS + 1, rays.shape[0], N1), generator=gen)
+        u = torch.rand((LAYERS + 1, rays.shape[0], N2), generator=gen)
         t0 = time.perf_counter()
         with torch.no_grad():
-            O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=0.0, bkgd_density_threshold=0.0)
+            O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append((rays.shape[0], dt))
@@ -156,11 +179,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="taekwondo2", choices=list(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "taekwondo 2-layer 1080p, 16 views, 64+128 samples (BASELINE configs[1])",
-              "step": "one 1080p view = 2073600 rays (view = step mod 16)", "layers": 3, "n1": N1, "n2": N2,
+    config = {"workload": WORKLOAD_NAME,
+              "step": "one %dx%d view = %d rays (view = step mod %d)" % (W, H, H * W, VIEWS), "layers": LAYERS + 1, "n1": N1, "n2": N2,
               "parallelism": "rows interleaved over %d GPU(s) + 1 all-gather of fine image planes per view" % world,
               "l2": "no explicit flush: per-chunk working set (~1.2 GB of samples/raw/σ buffers) >> 126 MB L2"}
 
@@ -192,11 +217,12 @@ def main():
 
     sd, data = load_weights()
     bkgd, frames, cams = scene_setup()
-    model = modeling.build_layered_model(make_cfg(LAYERS, N1, N2, True, args.precision))
+    model = modeling.build_layered_model(make_cfg(LAYERS, N1, N2, SPACE_TIME, args.precision))
     model.load_state_dict(sd)
     model.set_bkgd_bbox(bkgd); model.set_bboxes(frames)
     nat = model._ensure_native(dev)
-    nat.set_scene(model._resolve_scene(torch.tensor(FRAME_IDS), 0.0, 0.0))      # demo/taekwondo_demo.py:44 thresholds
+    model.near = NEAR
+    nat.set_scene(model._resolve_scene(torch.tensor(FRAME_IDS), THR[0], THR[1]))   # the demo's thresholds
     svr = ShardedViewRenderer(nat, H, W, N1, N2, rank, world)
     rays_dev = [svr.rays_for(K, T, FRAME_IDS) for (K, T) in cams]               # inputs resident in HBM
     n_local = rays_dev[0].shape[0]
@@ -238,8 +264,8 @@ def main():
     # the same views as the first steps of the timed region (cost depends on how many rays hit the performers)
     e2e_views = [(args.warmup + i) % VIEWS for i in range(max(1, args.e2e_steps))]
     rays_host = [rays_dev[v].cpu().pin_memory() for v in e2e_views]
-    out_host = torch.empty((2, 4, 5 * n_local), dtype=torch.float32).pin_memory()
-    mask_host = torch.empty((3, n_local), dtype=torch.uint8).pin_memory()
+    out_host = torch.empty((2, LAYERS + 2, 5 * n_local), dtype=torch.float32).pin_memory()
+    mask_host = torch.empty((LAYERS + 1, n_local), dtype=torch.uint8).pin_memory()
     nat.render_host(rays_host[0], N1, N2, seed=99, out_host=out_host, mask_host=mask_host)   # warm staging buffers
     torch.cuda.synchronize()
     if world > 1:
@@ -296,7 +322,7 @@ def main():
     # compositing kernel against the HBM roofline (algorithmic bytes: l*S*20 B in per ray-pass + outputs)
     cp = prof["composite"]
     hit_frac = max(0.0, pts - bk_pts) / max(1.0, bk_pts)
-    bytes_comp = float(n_local) * args.steps * ((1 + hit_frac) * (N1 * 24 + (N1 + N2) * 20) + 3 * (N1 + N2) * 4 + 160)
+    bytes_comp = float(n_local) * args.steps * ((1 + hit_frac) * (N1 * 24 + (N1 + N2) * 20 + (N1 + N2) * 4) + (LAYERS + 2) * 40)
     roof["composite_hbm"] = {"achieved_GBps": bytes_comp / (cp["ms"] * 1e-3) / 1e9 if cp["ms"] > 0 else 0.0,
                              "peak_GBps": peaks.get("hbm_gbs", 6650.0)}
 

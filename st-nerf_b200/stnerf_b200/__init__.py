@@ -10,6 +10,7 @@ from ._lib import StnerfError
 from .model import LayeredRFRender, build_layered_model, fresh_state_dict
 from .native import NativeRenderer, launch_count, split_planes
 from . import ops
+from .pose_renderer import PoseRenderer
 
 __all__ = ["LayeredRFRender", "build_layered_model", "fresh_state_dict", "NativeRenderer", "StnerfError", "ops",
-           "launch_count", "split_planes"]
+           "launch_count", "split_planes", "PoseRenderer"]

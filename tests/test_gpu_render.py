@@ -154,3 +154,37 @@ def test_row_sharded_render_equals_unsharded():
     both = assemble_image(torch.stack(parts, 0), H, W, 2)
     assert torch.equal(both, img)
     assert torch.isfinite(img).all() and img[0, ..., 4].max() <= 1 + 1e-5
+
+
+def test_pose_renderer_matches_forward_on_device_rays():
+    """render_pose fast path (device ray generation + one native call) returns what
+    LayeredNeuralRenderer.render_pose derives from layered_batchify_ray on the same rays."""
+    import utils
+    from oracle import stnerf_oracle as O
+    from stnerf_b200 import PoseRenderer, ops
+    name = "syn_L2_64_128"
+    case = C.CASES[name]
+    model = build_case_model(name, "exact")
+    H, W = 72, 64                                       # 4608 rays >= the 3584-ray chunk: thresholds are forwarded
+    K, T = O.synthetic_camera(3, 16, H, W)
+    pairs = [(0, 0), (1, 10), (2, 11)]
+    pr = PoseRenderer(model, H, W, far=20.0)
+    seed0 = model.seed
+    color, depth, color_layer, depth_layer = pr.render_pose(T, K, pairs, density_threshold=0.3, bkgd_density_threshold=0.05)
+    assert color.shape == (H, W, 3) and depth.shape == (H, W, 1) and len(color_layer) == 3 and depth_layer[2].shape == (H, W, 1)
+    # reference flow on the same (device-generated) rays and the same Philox seed
+    rays = ops.generate_rays(K, T, H, W, frame_ids=[0, 10, 11])
+    model.seed = seed0
+    with torch.no_grad():
+        stage2, stage1, stage2_layer, stage1_layer, _ = utils.layered_batchify_ray(
+            model, rays, torch.zeros(H * W, device="cuda"), None, density_threshold=0.3, bkgd_density_threshold=0.05)
+    assert torch.equal(color, stage2[0].reshape(H, W, 3))
+    d = stage2[1].reshape(H, W, 1).clone(); d[d < 0] = 0
+    assert torch.equal(depth, d / 20.0)
+    for i in range(3):
+        assert torch.equal(color_layer[i], stage2_layer[i][0].reshape(H, W, 3))
+        assert torch.equal(depth_layer[i], stage2_layer[i][1].reshape(H, W, 1) / 20.0)
+    # path form: asynchronous D2H, CPU tensors
+    frames = list(pr.render_path([T, T], [K, K], [pairs, pairs], density_threshold=0.3, bkgd_density_threshold=0.05))
+    assert len(frames) == 2 and not frames[0][0].is_cuda and frames[1][0].shape == (H, W, 3)
+    assert torch.isfinite(frames[1][0]).all()
