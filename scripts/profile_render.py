@@ -16,10 +16,11 @@ ap.add_argument("--rays", type=int, default=65536)
 ap.add_argument("--precision", default="exact")
 ap.add_argument("--calls", type=int, default=2)
 ap.add_argument("--warm", type=int, default=1)
+ap.add_argument("--chunk", type=int, default=0)
 a = ap.parse_args()
 sd, _ = B.load_weights()
 bkgd, frames, cams = B.scene_setup()
-m = modeling.build_layered_model(make_cfg(B.LAYERS, B.N1, B.N2, True, a.precision))
+m = modeling.build_layered_model(make_cfg(B.LAYERS, B.N1, B.N2, True, a.precision, a.chunk))
 m.load_state_dict(sd); m.set_bkgd_bbox(bkgd); m.set_bboxes(frames)
 dev = torch.device("cuda", 0)
 nat = m._ensure_native(dev)
@@ -34,6 +35,6 @@ nat.profile_begin()
 for i in range(a.calls):
     nat.render(rays, B.N1, B.N2, seed=100 + i)
 prof = nat.profile_end()
-print(json.dumps({"lib": os.environ.get("STNERF_B200_LIB", "default"), "rays": rays.shape[0], "calls": a.calls,
+print(json.dumps({"lib": os.environ.get("STNERF_B200_LIB", "default"), "rays": rays.shape[0], "calls": a.calls, "chunk": a.chunk,
                   "ms_per_call": {k: round(v["ms"] / a.calls, 3) for k, v in prof.items()},
                   "points": {k: v["points"] / a.calls for k, v in prof.items()}}))

@@ -11,6 +11,8 @@ from .model import LayeredRFRender, build_layered_model, fresh_state_dict
 from .native import NativeRenderer, launch_count, split_planes
 from . import ops
 from .pose_renderer import PoseRenderer
+from .camera_path import CameraPath
+from . import checkpoint_io
 
 __all__ = ["LayeredRFRender", "build_layered_model", "fresh_state_dict", "NativeRenderer", "StnerfError", "ops",
-           "launch_count", "split_planes", "PoseRenderer"]
+           "launch_count", "split_planes", "PoseRenderer", "CameraPath", "checkpoint_io"]

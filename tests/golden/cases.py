@@ -202,3 +202,36 @@ def function_inputs() -> dict:
     K, T = O.synthetic_camera(3, 16, 24, 40)
     d["rays.T"] = T
     return d
+
+
+# --------------------------------------------------------------------------- camera-path scenarios
+CAMERA_PATH_SCENARIOS = {
+    # demo/taekwondo_demo.py:41-52
+    "taekwondo": dict(offset=0, steps=101, around=False, smooth_time=False,
+                      retime=[(1, [21, 49, 74, 87], [20, 50, 74, 85]), (2, [13, 42, 80, 90], [20, 50, 74, 85])]),
+    # demo/walking_demo.py:46-50 (FRAME_OFFSET 25, pose duration [1,14), inverted path), one layer hidden
+    "walking": dict(offset=25, steps=100, around=False, smooth_time=False, pose_duration=(1, 14), invert=True, hidden=[1]),
+    # all cameras as rotation keys, fractional frame ids, edit schedules
+    "around_smooth": dict(offset=0, steps=37, around=True, smooth_time=True,
+                          s_shift=[[[0, 0, 0], [0, 0, 0], [0, 0, 0]], [[0, 0, 0], [0, 2, 0], [0, -2, 0]]],
+                          s_alpha=[1.0, 0.25]),
+}
+
+
+def camera_path_inputs():
+    """16 ground-truth cameras of the synthetic rig as the torch tensors the reference's dataset object holds."""
+    cams = [O.synthetic_camera(v, 16, 1080, 1920) for v in range(16)]
+    gt_poses = torch.stack([T for (_, T) in cams], 0)
+    gt_Ks = [K * (1.0 + 0.01 * i) for i, (K, _) in enumerate(cams)]
+    return gt_poses, gt_Ks
+
+
+def drive_camera_path(r, sc):
+    """The same call sequence for the reference class (golden generation) and for stnerf_b200.CameraPath (test)."""
+    if "pose_duration" in sc:
+        r.set_pose_duration(*sc["pose_duration"])
+    r.set_smooth_path_poses(sc["steps"], around=sc["around"], smooth_time=sc["smooth_time"])
+    for layer_id, kfl, kf in sc.get("retime", []):
+        r.retime_by_key_frames(layer_id, kfl, kf)
+    if sc.get("invert"):
+        r.invert_poses()

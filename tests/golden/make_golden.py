@@ -121,13 +121,60 @@ def run_functions():
     print("functions.npz: %d arrays" % len(out))
 
 
+def reference_path_class():
+    """The reference's camera-path / retiming methods, executed from its own source: the class cannot be imported
+    (module-level `from config import cfg`, imageio, robopy), so the FunctionDef nodes of the methods are lifted out of
+    render/layered_neural_renderer.py unchanged and compiled into a bare class."""
+    import ast
+    from scipy.spatial.transform import Rotation, Slerp
+    from scipy.interpolate import splprep, splev
+    src = open(os.path.join(R.REFERENCE_ROOT, "render", "layered_neural_renderer.py")).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LayeredNeuralRenderer"][0]
+    want = {"set_smooth_path_poses", "retime_by_key_frames", "set_frame_duration", "set_pose_duration", "invert_poses",
+            "is_shown_layer", "load_path_poses"}
+    cls.body = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    mod = ast.Module(body=[cls], type_ignores=[])
+    ns = {"np": np, "torch": torch, "R": Rotation, "Slerp": Slerp, "splprep": splprep, "splev": splev}
+    exec(compile(mod, "layered_neural_renderer.py", "exec"), ns)
+    return ns["LayeredNeuralRenderer"]
+
+
+def run_camera_path():
+    Ref = reference_path_class()
+    out = {}
+    for name, sc in C.CAMERA_PATH_SCENARIOS.items():
+        gt_poses, gt_Ks = C.camera_path_inputs()
+        r = Ref.__new__(Ref)
+        r.gt_poses, r.gt_Ks = gt_poses, gt_Ks
+        r.layer_num = 2
+        r.min_frame = [1 + sc["offset"]] * 3
+        r.max_frame = [101 + sc["offset"]] * 3
+        r.display_layers = {i: (0 if i in sc.get("hidden", []) else 1) for i in range(3)}
+        r.min_camera_id, r.max_camera_id = 0, gt_poses.shape[0] - 1
+        r.s_shift, r.s_scale, r.s_alpha = sc.get("s_shift"), sc.get("s_scale"), sc.get("s_alpha")
+        r.poses, r.Ks, r.layer_frame_pairs = [], [], []
+        C.drive_camera_path(r, sc)
+        out[name + ".poses"] = np.stack([np.asarray(p, dtype=np.float64) for p in r.poses])
+        out[name + ".Ks"] = np.stack([np.asarray(k, dtype=np.float64) for k in r.Ks])
+        out[name + ".pairs"] = np.array([[f for (_, f) in pair] for pair in r.layer_frame_pairs], dtype=np.float64)
+        if sc.get("s_shift") is not None:
+            out[name + ".s_shift_frame"] = np.array(r.s_shift_frame, dtype=np.float64)
+        if sc.get("s_alpha") is not None:
+            out[name + ".s_alpha_frame"] = np.array(r.s_alpha_frame, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "camera_path.npz"), **out)
+    print("camera_path.npz: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference (build container only)"
     torch.set_num_threads(os.cpu_count())
     stash_checkpoints()
-    names = sys.argv[1:] or (list(C.CASES) + ["functions"])
+    names = sys.argv[1:] or (list(C.CASES) + ["functions", "camera_path"])
     for nm in names:
         if nm == "functions":
             run_functions()
+        elif nm == "camera_path":
+            run_camera_path()
         else:
             run_case(nm)
