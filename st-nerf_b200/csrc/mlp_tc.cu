@@ -255,6 +255,14 @@ __device__ __forceinline__ Pt fetch_pt(const PointSrc& s, long long p, long long
   return q;
 }
 
+// Full-range sin/cos (Cody-Waite + Payne-Hanek slow path) as ONE out-of-line copy: inlining it at every encoding site
+// made the kernels 150-400 KB of SASS, far beyond the instruction cache.
+__device__ __noinline__ float2 sincos_full(float x) {
+  float s, c;
+  sincosf(x, &s, &c);
+  return make_float2(s, c);
+}
+
 // Write NV fp32 values of one row as fp16 hi (+lo) 16-byte chunks: columns col0 .. col0+NV-1 of an activation block
 // (col0 and NV multiples of 8).
 template <int NV>
@@ -276,88 +284,117 @@ __device__ __forceinline__ void store_row_split(uint8_t* hi_blk, int lo_stride, 
   }
 }
 
-// Input encoding of one row, written by the two threads (half = 0/1) that own the row.
-// Column order is a permutation of the reference's (utils/dimension_kernel.py:24-33) chosen so each thread owns whole
-// 16-byte chunks; the weight packer applies the same permutation (enc_perm_* below).
-//   SpaceNet (64 cols):  half 0 -> [x, y, f0..f4: sin xyz, cos xyz]   half 1 -> [z, f5..f9: sin xyz, cos xyz, 0]
-//   MotionNet (2 x 64):  half 0 -> chunk 0 [x,y,z,t, f0..f4: sin xyzt, cos xyzt, 0 x20]   half 1 -> chunk 1 [f5..f9 ..., 0 x24]
-template <int NET, int half>
-__device__ __forceinline__ void encode_row_half(uint8_t* smem, const Pt& pt, int row, bool exact, bool lerp) {
-  using S = Sched<NET>;
+// Input encoding of one row, written by the two threads (half = 0/1) that own the row, in PIECES that are spread over
+// the idle time the epilogue warps have between layers (each piece = whole 16-byte chunks of the swizzled block).
+// Column order is a permutation of the reference's (utils/dimension_kernel.py:24-33); the weight packer applies the
+// same permutation (enc_perm_* below).  With f_k = [sin(2^k x), sin(2^k y), sin(2^k z), cos ...] (6 values, SpaceNet)
+// or the 8-value xyzt analogue (MotionNet):
+//   SpaceNet, 64 cols : half 0 -> [f0 f1 f2 | f3 f4 x y]      half 1 -> [f5 f6 f7 | f8 f9 z 0]        (2 pieces of 16 cols)
+//   MotionNet, 2 x 64 : half h -> block h: chunk c<5 = f_(5h+c), chunk 5 = [x y z t 0 0 0 0] (h=0) / 0, chunks 6,7 = 0
+//                       pieces: {f_(5h), f_(5h+1)}, {f_(5h+2), f_(5h+3)}, {f_(5h+4), raw}
+template <int half, int piece>
+__device__ __forceinline__ void encode_space_piece(uint8_t* smem, const Pt& pt, int row, bool exact, float (&carry)[2]) {
+  using S = Sched<NET_SPACE>;
   uint8_t* enc = smem + S::enc_base;
-  if (NET == NET_SPACE) {
-    const float xs[3] = {pt.x, pt.y, pt.z};
-    float v[32];
-    int n = 0;
-    if (half == 0) { v[0] = xs[0]; v[1] = xs[1]; n = 2; } else { v[0] = xs[2]; n = 1; }
+  const float xs[3] = {pt.x, pt.y, pt.z};
+  float v[16];
+  auto trig = [&](int f, float* dst) {
+    const float fr = (float)(1 << f);
+    float sn[3], cs[3];
 #pragma unroll
-    for (int ff = 0; ff < 5; ++ff) {
-      const float fr = (float)(1 << (half * 5 + ff));
-      float sn[3], cs[3];
+    for (int d = 0; d < 3; ++d) { const float2 sc = sincos_full(xs[d] * fr); sn[d] = sc.x; cs[d] = sc.y; }
 #pragma unroll
-      for (int d = 0; d < 3; ++d) sincosf(xs[d] * fr, &sn[d], &cs[d]);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) { v[n + d] = sn[d]; v[n + 3 + d] = cs[d]; }
-      n += 6;
-    }
-    if (half == 1) v[31] = 0.f;
-    store_row_split<32>(enc, S::ENC_LO_STRIDE, row, half * 32, v, exact);
+    for (int d = 0; d < 3; ++d) { dst[d] = sn[d]; dst[3 + d] = cs[d]; }
+  };
+  if (piece == 0) {
+    float t3[6];
+    trig(5 * half + 0, v); trig(5 * half + 1, v + 6); trig(5 * half + 2, t3);
+    v[12] = t3[0]; v[13] = t3[1]; v[14] = t3[2]; v[15] = t3[3];
+    carry[0] = t3[4]; carry[1] = t3[5];
   } else {
-    const float lo_t = floorf(pt.tm), wgt = pt.tm - lo_t, omw = 1.0f - wgt;
-    const float in4[4] = {pt.x, pt.y, pt.z, pt.tm};
-    float v[64];
-    int n = 0;
-    if (half == 0) {
+    v[0] = carry[0]; v[1] = carry[1];
+    trig(5 * half + 3, v + 2); trig(5 * half + 4, v + 8);
+    v[14] = half == 0 ? xs[0] : xs[2];
+    v[15] = half == 0 ? xs[1] : 0.f;
+  }
+  store_row_split<16>(enc, S::ENC_LO_STRIDE, row, half * 32 + piece * 16, v, exact);
+}
+
+template <int half, int piece>
+__device__ __forceinline__ void encode_motion_piece(uint8_t* smem, const Pt& pt, int row, bool exact, bool lerp) {
+  using S = Sched<NET_MOTION>;
+  uint8_t* enc = smem + S::enc_base + half * ABLOCK;
+  const float lo_t = floorf(pt.tm), wgt = pt.tm - lo_t, omw = 1.0f - wgt;
+  const float in4[4] = {pt.x, pt.y, pt.z, pt.tm};
+  auto trig = [&](int f, float* dst) {
+    const float fr = (float)(1 << f);
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        float a = in4[d];
-        if (lerp) {      // (1-w)*PE([xyz, floor t]) + w*PE([xyz, floor t + 1]) column by column (motion_net.py:63)
+    for (int d = 0; d < 4; ++d) {
+      float sn, cs;
+      if (!lerp) {
+        const float2 sc = sincos_full(in4[d] * fr);
+        sn = sc.x; cs = sc.y;
+      } else {     // (1-w)*PE([xyz, floor t]) + w*PE([xyz, floor t + 1]) column by column (motion_net.py:63)
+        const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? a : lo_t + 1.0f;
+        const float2 sc0 = sincos_full(a * fr), sc1 = sincos_full(b2 * fr);
+        sn = __fadd_rn(__fmul_rn(omw, sc0.x), __fmul_rn(wgt, sc1.x));
+        cs = __fadd_rn(__fmul_rn(omw, sc0.y), __fmul_rn(wgt, sc1.y));
+      }
+      dst[d] = sn; dst[4 + d] = cs;
+    }
+  };
+  float v[16];
+  trig(5 * half + 2 * piece, v);
+  if (piece < 2) {
+    trig(5 * half + 2 * piece + 1, v + 8);
+  } else {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float a = 0.f;
+      if (half == 0) {
+        a = in4[d];
+        if (lerp) {
           const float lo = d < 3 ? in4[d] : lo_t, hi = d < 3 ? in4[d] : lo_t + 1.0f;
           a = __fadd_rn(__fmul_rn(omw, lo), __fmul_rn(wgt, hi));
         }
-        v[d] = a;
       }
-      n = 4;
+      v[8 + d] = a; v[12 + d] = 0.f;
     }
-#pragma unroll
-    for (int ff = 0; ff < 5; ++ff) {
-      const float fr = (float)(1 << (half * 5 + ff));
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        float sn, cs;
-        if (!lerp) {
-          sincosf(in4[d] * fr, &sn, &cs);
-        } else {
-          const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? a : lo_t + 1.0f;
-          float s0, c0, s1, c1;
-          sincosf(a * fr, &s0, &c0);
-          sincosf(b2 * fr, &s1, &c1);
-          sn = __fadd_rn(__fmul_rn(omw, s0), __fmul_rn(wgt, s1));
-          cs = __fadd_rn(__fmul_rn(omw, c0), __fmul_rn(wgt, c1));
-        }
-        v[n + d] = sn; v[n + 4 + d] = cs;
-      }
-      n += 8;
-    }
-#pragma unroll
-    for (int i = 0; i < 64; ++i) if (i >= (half == 0 ? 44 : 40)) v[i] = 0.f;
-    store_row_split<64>(enc + half * ABLOCK, S::ENC_LO_STRIDE, row, 0, v, exact);
   }
-}
-template <int NET>
-__device__ __forceinline__ void encode_row(uint8_t* smem, const Pt& pt, int row, int half, bool exact, bool lerp) {
-  if (half == 0) encode_row_half<NET, 0>(smem, pt, row, exact, lerp);
-  else encode_row_half<NET, 1>(smem, pt, row, exact, lerp);
+  store_row_split<16>(enc, S::ENC_LO_STRIDE, row, piece * 16, v, exact);
 }
 
-// One 64-column chunk of a hidden layer's epilogue for this thread's row: 32 accumulator columns (column half hh)
-// -> bias + ReLU (+ optional fp32 dot with a head weight vector) -> fp16 hi/lo -> 16-byte stores -> release to the MMA warp.
+// piece dispatcher (half is warp-uniform)
+template <int NET, int piece>
+__device__ __forceinline__ void encode_piece(uint8_t* smem, const Pt& pt, int row, int half, bool exact, bool lerp,
+                                             float (&carry)[2]) {
+  if (NET == NET_SPACE) {
+    if (half == 0) encode_space_piece<0, piece < 2 ? piece : 1>(smem, pt, row, exact, carry);
+    else encode_space_piece<1, piece < 2 ? piece : 1>(smem, pt, row, exact, carry);
+  } else {
+    if (half == 0) encode_motion_piece<0, piece>(smem, pt, row, exact, lerp);
+    else encode_motion_piece<1, piece>(smem, pt, row, exact, lerp);
+  }
+}
+
+#ifdef STNERF_TIMING
+struct EpiTiming { long long ld = 0, math = 0, fence = 0, arrive = 0, wait_dfull = 0, n = 0, enc = 0, last_wait = 0, last_epi = 0, tiles = 0; };
+#define TSTAMP(x) const long long x = clock64()
+#else
+#define TSTAMP(x)
+#endif
+
 template <bool SIGMA>
 __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, int row, const float* __restrict__ bias,
                                                   const float* __restrict__ wdot, uint8_t* blk, int lo_stride, bool exact,
-                                                  int lane, uint32_t ready_bar, float dot) {
+                                                  int lane, uint32_t ready_bar, float dot
+#ifdef STNERF_TIMING
+                                                  , EpiTiming& tm
+#endif
+) {
   uint32_t acc[32];
   const int col0 = j * 64 + hh * 32;
+  TSTAMP(t0);
   tmem_ld32_issue(dcol + (uint32_t)col0, acc);
   float4 bv[8], wv[8];
   {
@@ -371,6 +408,7 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
     }
   }
   tmem_ld_wait(acc);
+  TSTAMP(t1);
 #pragma unroll
   for (int gq = 0; gq < 4; ++gq) {                     // 8 columns -> one 16-byte chunk
     uint32_t hp[4], lp[4];
@@ -396,9 +434,15 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
     *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
     if (exact) *reinterpret_cast<uint4*>(blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
+  TSTAMP(t2);
   fence_proxy_async();
   __syncwarp();
+  TSTAMP(t3);
   if (lane == 0) mbar_arrive(ready_bar);
+#ifdef STNERF_TIMING
+  const long long t4 = clock64();
+  tm.ld += t1 - t0; tm.math += t2 - t1; tm.fence += t3 - t2; tm.arrive += t4 - t3; tm.n += 1;
+#endif
   return dot;
 }
 
@@ -524,16 +568,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
     const float* bias_all = P.aux + AUX_BIAS;
     const bool lerp = (NET == NET_MOTION) && (P.lerp_force >= 0 ? (P.lerp_force != 0) : (P.lerp_flag && *P.lerp_flag != 0));
     uint32_t g = 0;
+#ifdef STNERF_TIMING
+    EpiTiming tm;
+    const long long t_begin = clock64();
+#endif
 
     // encoding of the first tile
     Pt cur = fetch_pt(P.src, (long long)blockIdx.x * TILE_M + row, n_points);
+    float carry[2] = {0.f, 0.f};
+    if (NET == NET_MOTION) {
+      // zero padding of the MotionNet encoding blocks (chunks 5.. of block 1, 6.. of block 0): written once, never touched again
+      uint8_t* enc = smem + S::enc_base + hh * ABLOCK;
+      for (int c = (hh == 0 ? 48 : 40); c < 64; c += 8) {
+        const uint32_t off = sw128_offset(row, c);
+        *reinterpret_cast<uint4*>(enc + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(enc + S::ENC_LO_STRIDE + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
     if ((long long)blockIdx.x < n_tiles) {
-      encode_row<NET>(smem, cur, row, hh, exact, lerp);
+      encode_piece<NET, 0>(smem, cur, row, hh, exact, lerp, carry);
+      encode_piece<NET, 1>(smem, cur, row, hh, exact, lerp, carry);
+      if (NET == NET_MOTION) encode_piece<NET, 2>(smem, cur, row, hh, exact, lerp, carry);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
     }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long nt = tile + gridDim.x;
+      const bool have_next = nt < n_tiles;
       Pt nxt = cur;
       float sig_dot = 0.f;
       for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
@@ -543,56 +605,103 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
         const float* bias = bias_all + l * 256;
         const uint32_t dcol = lane_taddr + b * 256;
         if (!last) {
+          TSTAMP(tw0);
           mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
           tc_fence_after();
+#ifdef STNERF_TIMING
+          tm.wait_dfull += clock64() - tw0;
+#endif
           const int nchunk = width / 64;
           if (NET == NET_SPACE && l == 6) {
             for (int j = 0; j < nchunk; ++j)
               sig_dot = epi_hidden_chunk<true>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
-                                               S::LO_STRIDE, exact, lane, BAR(BAR_AREADY + j), sig_dot);
+                                               S::LO_STRIDE, exact, lane, BAR(BAR_AREADY + j), sig_dot
+#ifdef STNERF_TIMING
+                                               , tm
+#endif
+              );
           } else {
             for (int j = 0; j < nchunk; ++j)
               epi_hidden_chunk<false>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, exact,
-                                      lane, BAR(BAR_AREADY + j), 0.f);
+                                      lane, BAR(BAR_AREADY + j), 0.f
+#ifdef STNERF_TIMING
+                                      , tm
+#endif
+              );
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
-          if (l == S::ENC_LAST_USE) {
-            // the MMAs of this layer were the last readers of the encoding buffer (their completion was observed through
-            // d_full above): write the next tile's encoding now, overlapped with the MMAs of the following layers
-            const long long nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-              nxt = fetch_pt(P.src, nt * TILE_M + row, n_points);
-              encode_row<NET>(smem, nxt, row, hh, exact, lerp);
+          // Idle time until the next accumulator is ready: fetch and encode the NEXT tile's points piece by piece.
+          // The encoding buffer is free once the MMAs of layer ENC_LAST_USE are done (observed through d_full above).
+          //   SpaceNet : fetch after layer 1, pieces after layers 4 and 5
+          //   MotionNet: fetch after layer 0, pieces after layers 1, 2, 3
+          if (have_next) {
+            TSTAMP(te0);
+            constexpr int L_FETCH = (NET == NET_SPACE) ? 1 : 0;
+            constexpr int L_P0 = (NET == NET_SPACE) ? 4 : 1;
+            if (l == L_FETCH) nxt = fetch_pt(P.src, nt * TILE_M + row, n_points);
+            if (l == L_P0) encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
+            if (l == L_P0 + 1) encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
+            if (NET == NET_MOTION && l == L_P0 + 2) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
+            if (l == L_P0 + (NET == NET_SPACE ? 1 : 2)) {
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
             }
+#ifdef STNERF_TIMING
+            tm.enc += clock64() - te0;
+#endif
           }
         } else {
           // last layer: 128 features -> 3-wide head in fp32 (rgb_net.3 / motion_net.10).
           // SpaceNet: the bias is the per-ray vector of head_bias_kernel (dir/time part of rgb_net.1 + b1).
           const float* brow = (NET == NET_SPACE) ? (P.cbuf + (size_t)cur.cidx * 128) : bias;
+          TSTAMP(tl0);
+          float4 bb4[8];                                           // per-ray bias row: L2-resident, fetched ahead of the wait
+          {
+            const float4* bp = reinterpret_cast<const float4*>(brow + hh * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bb4[i] = __ldg(bp + i);
+          }
           mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
           tc_fence_after();
+          TSTAMP(tl1);
           float dot3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
           for (int j = 0; j < 2; ++j) {
             uint32_t acc[32];
             const int col0 = j * 64 + hh * 32;
             tmem_ld32_issue(dcol + (uint32_t)col0, acc);
-            float4 bb4[8];
-            const float4* bp = reinterpret_cast<const float4*>(brow + col0);
+            float4 bn4[8];
+            if (j == 0) {
+              const float4* bp = reinterpret_cast<const float4*>(brow + 64 + hh * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) bb4[i] = __ldg(bp + i);
+              for (int i = 0; i < 8; ++i) bn4[i] = __ldg(bp + i);
+            }
             tmem_ld_wait(acc);
+            float v[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float4 bb = bb4[c >> 2];
               const float bc = (c & 3) == 0 ? bb.x : (c & 3) == 1 ? bb.y : (c & 3) == 2 ? bb.z : bb.w;
-              const float v = fmaxf(__uint_as_float(acc[c]) + bc, 0.f);
+              v[c] = fmaxf(__uint_as_float(acc[c]) + bc, 0.f);
+            }
 #pragma unroll
-              for (int o = 0; o < 3; ++o) dot3[o] = fmaf(v, __ldg(P.aux + AUX_WOUT + o * 128 + col0 + c), dot3[o]);
+            for (int o = 0; o < 3; ++o) {
+              const float4* wp = reinterpret_cast<const float4*>(P.aux + AUX_WOUT + o * 128 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 ww = __ldg(wp + i);
+                dot3[o] = fmaf(v[4 * i], ww.x, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 1], ww.y, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 2], ww.z, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 3], ww.w, dot3[o]);
+              }
+            }
+            if (j == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bb4[i] = bn4[i];
             }
           }
           tc_fence_before();
@@ -625,10 +734,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
             }
           }
           epi_bar_sync();       // s_part is rewritten by the next tile
+#ifdef STNERF_TIMING
+          tm.last_wait += tl1 - tl0; tm.last_epi += clock64() - tl1; tm.tiles += 1;
+#endif
         }
       }
       cur = nxt;
     }
+#ifdef STNERF_TIMING
+    if (blockIdx.x == 0 && lane == 0 && tm.n > 0)
+      printf("[timing net %d warp %d] chunks %lld | per chunk: ld %lld math %lld fence %lld arrive %lld | d_full wait per layer %lld | total cycles %lld\n",
+             NET, warp, tm.n, tm.ld / tm.n, tm.math / tm.n, tm.fence / tm.n, tm.arrive / tm.n, tm.wait_dfull * 4 / tm.n, clock64() - t_begin);
+    if (blockIdx.x == 0 && lane == 0 && tm.tiles > 0 && warp == 4)
+      printf("[timing net %d] tiles %lld | per tile: encode %lld, last-layer wait %lld, last-layer epilogue %lld, total %lld\n", NET, tm.tiles,
+             tm.enc / tm.tiles, tm.last_wait / tm.tiles, tm.last_epi / tm.tiles, (clock64() - t_begin) / tm.tiles);
+#endif
   }
   // teardown
   tc_fence_before();
@@ -768,20 +888,24 @@ std::vector<int> iota_chunk(int k0, int kend) {
   for (int i = 0; i < 64 && k0 + i < kend; ++i) c[i] = k0 + i;
   return c;
 }
-// encoding-buffer column -> reference PE column (see encode_row)
+// encoding-buffer column -> reference PE column (see encode_space_piece / encode_motion_piece).
+// Reference order (utils/dimension_kernel.py:24-33): raw (d), then per frequency f: sin (d values), cos (d values).
 std::vector<int> enc_perm_space(int base) {
   std::vector<int> c(64, -1);
-  c[0] = base + 0; c[1] = base + 1;
-  for (int i = 0; i < 30; ++i) c[2 + i] = base + 3 + i;            // f0..f4
-  c[32] = base + 2;
-  for (int i = 0; i < 30; ++i) c[33 + i] = base + 33 + i;          // f5..f9
+  for (int h = 0; h < 2; ++h) {
+    for (int ff = 0; ff < 5; ++ff)
+      for (int j = 0; j < 6; ++j) c[h * 32 + 6 * ff + j] = base + 3 + 6 * (5 * h + ff) + j;
+    if (h == 0) { c[30] = base + 0; c[31] = base + 1; } else { c[62] = base + 2; }
+  }
   return c;
 }
 std::vector<std::vector<int>> enc_perm_motion() {
-  std::vector<int> c0(64, -1), c1(64, -1);
-  for (int i = 0; i < 44; ++i) c0[i] = i;
-  for (int i = 0; i < 40; ++i) c1[i] = 44 + i;
-  return {c0, c1};
+  std::vector<std::vector<int>> out(2, std::vector<int>(64, -1));
+  for (int h = 0; h < 2; ++h)
+    for (int ff = 0; ff < 5; ++ff)
+      for (int j = 0; j < 8; ++j) out[h][8 * ff + j] = 4 + 8 * (5 * h + ff) + j;
+  for (int d = 0; d < 4; ++d) out[0][40 + d] = d;
+  return out;
 }
 
 int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vector<float>& aux, size_t expect_bytes) {
