@@ -161,11 +161,12 @@ def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
         u = torch.rand((LAYERS + 1, rays.shape[0], N2), generator=gen)
         t0 = time.perf_counter()
         with torch.no_grad():
-            O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
+            out = O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append((rays.shape[0], dt))
     n = sum(a for a, _ in times); t = sum(b for _, b in times)
+    cpu_reference_rate.last = (rays, jit, u, out)      # the parity leg of main() re-renders these rays on the GPU
     return n / t, t / len(times) * 1e3, rays.shape[0], data, threads
 
 
@@ -332,13 +333,29 @@ def main():
         cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                "sample": "3 steps x %d rays (4 row bands of the view), full 64+128 path, torch fp32, %d of %d host threads (fastest of a probe)" % (nr, cores, os.cpu_count() or 1)}
 
+    parity = None
+    if cpu is not None and getattr(cpu_reference_rate, "last", None) is not None:
+        # same rays / weights / uniforms through the GPU path vs the CPU oracle (itself pinned to the reference)
+        rays_c, jit_c, u_c, want = cpu_reference_rate.last
+        nat.set_ray_ids(0, 0, 0)
+        outp, _ = nat.render(rays_c.to(dev), N1, N2, jitter=jit_c.to(dev).contiguous(), u=u_c.to(dev).contiguous(), seed=1)
+        fm, _, _, _ = S.split_planes(outp, LAYERS + 1)
+        got = fm[0].float().cpu()
+        ref = want["fine_mixed"][0]
+        err = (got - ref).abs().max(dim=1)[0]
+        mse = float(((got - ref) ** 2).mean())
+        parity = {"rays": int(rays_c.shape[0]), "max_abs_rgb_err": float(err.max()),
+                  "frac_pixels_over_1e-3": float((err > 1e-3).float().mean()),
+                  "psnr_db": (99.0 if mse == 0 else float(10.0 * __import__("math").log10(1.0 / mse))),
+                  "against": "CPU oracle port (pinned to the reference by tests/golden), identical rays/weights/uniforms"}
+
     dtype = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate"}[args.precision]
     print(json.dumps({"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": dtype,
                       "data": "synthetic scene + cameras (SURVEY 8d); " + data, "config": config, "clocks": clk,
                       "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                      "precision": args.precision}))
+                      "parity": parity, "precision": args.precision}))
     if world > 1:
         dist.destroy_process_group()
 
