@@ -78,6 +78,8 @@ typedef struct {
   float bkgd_density_threshold;                  /* (:538-547)                                                  */
   float boarder_weight;                          /* cfg.MODEL.BOARDER_WEIGHT, last delta (render_layer.py:38)   */
   int32_t apply_thresholds;                      /* 1 in the retiming branch (:416,538,564), else 0             */
+  int32_t shared_frame_id;                       /* 1: 7-column rays [o,d,frame_id] of the evaluator (:157-158,171):   */
+                                                 /* every layer reads column 6; 0: one column per layer (retiming)      */
 } stnerf_scene;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
@@ -102,7 +104,7 @@ int stnerf_set_scene(stnerf_handle h, const stnerf_scene* scene_host);
 
 /* ---- the hot path: LayeredRFRender.forward (layered_rfrender.py:141-734), BBOX sampling ---------------- */
 /* rays: (n_rays, ray_stride) fp32, columns [o(3), d(3), frame_id_layer0 .. frame_id_layer(l-1)]
- *       (data/datasets/ray_dataset.py:276-281); ray_stride >= 6 + l.
+ *       (data/datasets/ray_dataset.py:276-281); ray_stride >= 6 + l  (>= 7 with scene.shared_frame_id).
  * jitter: (l, n_rays, n1) uniforms for layers/RaySamplePoint.py:98, or NULL -> in-kernel Philox(seed).
  * u:      (l, n_rays, n2) uniforms for utils/sample_pdf.py:31, or NULL -> Philox(seed).
  * out:    [2 passes: 0 coarse, 1 fine][l+1 images: 0 mixed, 1+i layer i] planes of 5*n_rays floats each,

@@ -231,7 +231,7 @@ def _inverse_edit(xyz, i, scale, shift, pivot, fine: bool):
 # --------------------------------------------------------------------------- a2..a13
 def render(nets: dict, scene: dict, rays: torch.Tensor, n1: int, n2: int,
            jitter: torch.Tensor, u: Optional[torch.Tensor], only_coarse: bool = False,
-           density_threshold: float = 1e-4, bkgd_density_threshold: float = 0.0) -> dict:
+           density_threshold: float = 1e-4, bkgd_density_threshold: float = 0.0, shared_frame: bool = False) -> dict:
     """modeling/layered_rfrender.py:141-734, retiming (render-time) branch, BBOX sampling.
 
     rays (N, 6+l) fp32; jitter (l,N,n1); u (l,N,n2).
@@ -240,8 +240,13 @@ def render(nets: dict, scene: dict, rays: torch.Tensor, n1: int, n2: int,
     """
     rays = rays.to(F32)
     o, d = rays[:, :3], rays[:, 3:6]
-    fid = rays[:, 6:]
     l = scene["bmin"].shape[0]
+    fid = rays[:, 6:]
+    if shared_frame:
+        # 7-column evaluator rays [o,d,frame_id] (:157-158,171): every layer reads the same column, boxes come from
+        # index_select(frame_id - 1) (:193) and the density thresholds are skipped (`if self.retiming`, :416,538,564)
+        fid = rays[:, 6:7].expand(-1, l)
+        density_threshold = bkgd_density_threshold = float("-inf")
     N = rays.shape[0]
     scale, shift, pivot = scene.get("scale"), scene.get("shift"), scene.get("pivot")
     shown = scene.get("shown", [True] * l)

@@ -280,6 +280,7 @@ int stnerf_set_scene(stnerf_handle c, const stnerf_scene* s) {
   d.near_plane = s->near_plane; d.alpha2 = s->alpha_layer2;
   d.thr_layer = s->density_threshold; d.thr_bkgd = s->bkgd_density_threshold;
   d.boarder = s->boarder_weight; d.apply_thr = s->apply_thresholds; d.n_layers = c->l;
+  d.fid_shared = s->shared_frame_id;
   c->have_scene = true;
   return STNERF_OK;
 }
@@ -334,7 +335,7 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     s.mode = SRC_MARCH;
     s.rays = rays; s.ray_stride = ray_stride;
     s.t = tbuf + i * tl;
-    s.S = S; s.layer = i;
+    s.S = S; s.layer = c->scene.shared_frame_id ? 0 : i;      // frame-id column offset of this layer
     s.pos_stride = 3; s.time_stride = 1;
     fill_edit(s, c->scene, i, fine);
     float* raw = rawbuf + (size_t)i * tl * 4;
@@ -364,7 +365,7 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
                   const float* jitter, const float* u, uint64_t seed, float* out, uint8_t* ray_mask, void* stream) {
   if (!c || !rays || !out || n_rays < 0) return STNERF_EINVAL;
   if (!c->have_scene) return STNERF_EINVAL;
-  if (ray_stride < 6 + c->l) return STNERF_EINVAL;              // the reference prints + exit(-1) (:162-163)
+  if (ray_stride < 6 + (c->scene.shared_frame_id ? 1 : c->l)) return STNERF_EINVAL;   // the reference prints + exit(-1) (:162-163)
   if (n1 < 3 || n1 > STNERF_MAX_N1) return STNERF_EINVAL;
   if (only_coarse) n2 = 0;
   if (n2 < 0 || n1 + n2 > STNERF_MAX_S) return STNERF_EINVAL;

@@ -110,6 +110,7 @@ struct DevScene {
   float near_plane, alpha2, thr_layer, thr_bkgd, boarder;
   int apply_thr;
   int n_layers;
+  int fid_shared;            // all layers read frame-id column 6 (7-column rays)
 };
 
 // ---------------------------------------------------------------------------------------------------------

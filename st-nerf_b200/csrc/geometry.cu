@@ -91,7 +91,7 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
     // (stored for phase 1b in a register: popc of lower lanes)
     if (h && i > 0) {
       // MotionNet's batch-global "any fractional frame id" test (modeling/motion_net.py:53)
-      const float f = rays[r * ray_stride + 6 + i];
+      const float f = rays[r * ray_stride + 6 + (scene.fid_shared ? 0 : i)];
       if (floorf(f) != f) atomicOr(&lerp_flags[i], 1);
     }
   }

@@ -31,7 +31,7 @@ class Scene(C.Structure):
                 ("scale", C.c_float * MAX_LAYERS), ("pivot", C.c_float * 3),
                 ("near_plane", C.c_float), ("alpha_layer2", C.c_float), ("density_threshold", C.c_float),
                 ("bkgd_density_threshold", C.c_float), ("boarder_weight", C.c_float),
-                ("apply_thresholds", C.c_int32)]
+                ("apply_thresholds", C.c_int32), ("shared_frame_id", C.c_int32)]
 
 
 class Profile(C.Structure):

@@ -155,8 +155,11 @@ class LayeredRFRender(torch.nn.Module):
         self.bboxes = table                                               # what .cuda() would have kept on the model
         boxes = [bk[0].clone()]
         for i in range(self.layer_num):
-            f = torch.tensor(float(frame_ids_row0[i + 1]), dtype=torch.float32) - 1           # (:200)
-            boxes.append(self.bbox_interpolation(f, i))
+            if self.retiming:
+                f = torch.tensor(float(frame_ids_row0[i + 1]), dtype=torch.float32) - 1       # (:200)
+                boxes.append(self.bbox_interpolation(f, i))
+            else:                                                         # index_select(int64(frame_id) - 1) (:193)
+                boxes.append(table[int(float(frame_ids_row0[i + 1])) - 1, i])
         boxes = torch.stack(boxes, 0)                                     # (l,8,3)
         first = torch.cat([bk, table[0]], 0)                              # (:216-220)
         centre = first.mean(1)
@@ -209,6 +212,7 @@ class LayeredRFRender(torch.nn.Module):
         sc.bkgd_density_threshold = float(bkgd_density_threshold)
         sc.boarder_weight = self.boarder_weight
         sc.apply_thresholds = 1 if self.retiming else 0
+        sc.shared_frame_id = 0 if self.retiming else 1
         return sc
 
     def _ensure_native(self, device):
@@ -230,8 +234,12 @@ class LayeredRFRender(torch.nn.Module):
         if width == 7 + self.layer_num:
             self.retiming = True                                         # (:159-160)
         elif width == 7:
-            raise NotImplementedError("7-column training rays (per-ray bbox lookup, layered_rfrender.py:193) are "
-                                      "outside the render hot path; pass [o,d,frame_id_0..frame_id_L] rays")
+            # evaluator rays [o,d,frame_id] (engine/layered_trainer.py:36,383): boxes by frame id (:193), no thresholds.
+            # One image per call shares its frame id; mixed-frame training batches are outside the render hot path.
+            self.retiming = False                                        # (:157-158)
+            if not bool((rays[:, 6] == rays[0, 6]).all()):
+                raise NotImplementedError("7-column rays with per-ray frame ids (training batches, per-ray bbox lookup "
+                                          "layered_rfrender.py:193) are outside the render hot path")
         else:
             raise ValueError("undefined ray format in LayeredRFRender, ray dimension is %d" % width)   # (:162-163)
         if not rays.is_cuda:
@@ -241,6 +249,8 @@ class LayeredRFRender(torch.nn.Module):
         rays = rays.detach().to(torch.float32)
         nat = self._ensure_native(rays.device)
         frame_ids = rays[0, 6:].cpu()                                    # boxes come from ray 0 only (:195-200)
+        if not self.retiming:
+            frame_ids = frame_ids[:1].expand(l)                          # index_select(frame_id - 1) for every layer (:193)
         nat.set_scene(self._resolve_scene(frame_ids, density_threshold, bkgd_density_threshold))
         jitter, u = self._inject if self._inject is not None else (None, None)
         self._inject = None

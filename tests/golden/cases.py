@@ -39,6 +39,9 @@ CASES = {
     # demo/walking_demo.py:43-50: thresholds 20/0.8, near=4; reference sample counts 90+30; layer 1 hidden
     "walk_90_30_hide": dict(weights="walking", L=2, space_time=False, n1=90, n2=30,
                             frame_ids=[0, 30, 31], thr=(20.0, 0.8), near=4.0, hidden=[1], n_rays=160, ray_seed=5),
+    # evaluator layout: 7-column rays [o,d,frame_id], boxes by index_select, no thresholds (engine/layered_trainer.py:36,383)
+    "tkd_eval_7col": dict(weights="taekwondo", L=2, space_time=True, n1=64, n2=128, seven=True,
+                          frame_ids=[10, 10, 10], thr=(20.0, 0.8), n_rays=128, ray_seed=8),
     # BASELINE config #3 flavour: walking nets replicated round-robin to 4 performer layers
     "walk_L4_64_128": dict(weights="walking", L=4, space_time=False, n1=64, n2=128,
                            frame_ids=[0, 30, 31, 32, 33], thr=(20.0, 0.8), near=4.0, n_rays=128, ray_seed=6),
@@ -110,7 +113,8 @@ def rays_for(case: dict) -> torch.Tensor:
         dvec = p - eye
         aimed.append(torch.cat([eye, dvec / dvec.norm()]))
     rays = torch.cat([grid, torch.stack(aimed, 0)], 0)
-    fid = torch.tensor(case["frame_ids"], dtype=torch.float32)[None].expand(n, -1)
+    ids = case["frame_ids"][:1] if case.get("seven") else case["frame_ids"]
+    fid = torch.tensor(ids, dtype=torch.float32)[None].expand(n, -1)
     return torch.cat([rays, fid], 1).contiguous()
 
 

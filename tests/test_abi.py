@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     L = _lib()
     # sizes implied by include/stnerf.h with STNERF_MAX_LAYERS = 8
     assert ctypes.sizeof(L.ModelDesc) == 4 + 4 * 8 + 4 + 4
-    assert ctypes.sizeof(L.Scene) == (96 + 96) + 32 + 32 + 96 + 32 + 32 + 32 + 12 + 5 * 4 + 4
+    assert ctypes.sizeof(L.Scene) == (96 + 96) + 32 + 32 + 96 + 32 + 32 + 32 + 12 + 5 * 4 + 4 + 4
     hdr = open(os.path.join(ROOT, "include", "stnerf.h")).read()
     assert "#define STNERF_MAX_LAYERS %d" % L.MAX_LAYERS in hdr
     assert "#define STNERF_MAX_N1 %d" % L.MAX_N1 in hdr

@@ -103,7 +103,8 @@ def test_render_case(name):
     jit, u = C.uniforms_for(case)
     out = O.render(nets, C.scene_for(case), C.rays_for(case), case["n1"], case["n2"], jit, u,
                    only_coarse=case.get("only_coarse", False),
-                   density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+                   density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1],
+                   shared_frame=case.get("seven", False))
     flat = C.flatten_outputs(out["fine_mixed"], out["coarse_mixed"], out["fine_layer"], out["coarse_layer"],
                              out["ray_mask"])
     assert set(flat) == set(gold)
