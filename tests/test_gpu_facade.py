@@ -75,3 +75,13 @@ def test_walking_demo_import_alias():
     from tests_support import make_cfg
     m = modeling.build_model(make_cfg(2, 64, 128, False))       # demo/walking_demo.py:18 imports this name
     assert m.state_dict()["spacenets.0.rgb_net.1.weight"].shape == (128, 283)
+
+
+def test_example_demo_runs(tmp_path):
+    """The scripted edit sessions of demo/taekwondo_demo.py on the B200 path (tiny size)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "taekwondo_demo_b200.py"), "--size", "96x54",
+                        "--steps", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert r.stdout.count("frames of 96x54") == 3
