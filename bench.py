@@ -63,19 +63,19 @@ def select_workload(name):
 
 def load_weights():
     import torch
-    import cases as C
-    p = C.find_checkpoint(CKPT)
+    from stnerf_b200 import checkpoint_io
+    p = checkpoint_io.find_checkpoint(CKPT)
     if p is not None:
-        sd = C.replicate_layers(torch.load(p, map_location="cpu")["model"], LAYERS)
+        sd = checkpoint_io.replicate_layers(torch.load(p, map_location="cpu")["model"], LAYERS)
         return sd, "%s checkpoint (oracle/_ref/ckpt)%s" % (CKPT, ", nets replicated round-robin to %d performers" % LAYERS if LAYERS > 2 else "")
-    from oracle import stnerf_oracle as O          # seeded weights only; nothing is computed by the oracle here
-    return O.synthetic_state_dict(LAYERS, SPACE_TIME, seed=7), "seeded random weights (checkpoint copy absent)"
+    from stnerf_b200 import synthetic
+    return synthetic.synthetic_state_dict(LAYERS, SPACE_TIME, seed=7), "seeded random weights (checkpoint copy absent)"
 
 
 def scene_setup():
-    from oracle import stnerf_oracle as O          # synthetic scene description shared with the tests (inputs only)
-    bkgd, frames = O.synthetic_boxes(LAYERS)
-    cams = [O.synthetic_camera(v, VIEWS, H, W) for v in range(VIEWS)]
+    from stnerf_b200 import synthetic              # synthetic scene description (inputs only)
+    bkgd, frames = synthetic.synthetic_boxes(LAYERS)
+    cams = [synthetic.synthetic_camera(v, VIEWS, H, W) for v in range(VIEWS)]
     return bkgd, frames, cams
 
 
@@ -118,8 +118,7 @@ class ClockSampler:
 def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
     """The reference algorithm on the host cores: oracle port (kind 'port'), bounded sample per step."""
     import torch
-    from oracle import stnerf_oracle as O
-    import cases as C
+    from oracle import stnerf_oracle as O          # the CPU leg is the one place bench.py executes the oracle
     sd, data = load_weights()
     nets = O.split_state_dict(sd, LAYERS)
     bkgd, frames, cams = scene_setup()
@@ -213,7 +212,7 @@ def main():
     import stnerf_b200 as S
     from stnerf_b200.dist import ShardedViewRenderer
     from stnerf_b200 import _lib as L
-    from tests_support import make_cfg
+    from stnerf_b200.config import make_cfg
     import modeling
 
     sd, data = load_weights()

@@ -17,15 +17,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "st-nerf_b200"))      # ahead of a reference checkout: B200 modeling/utils/layers/engine
-sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden")); sys.path.insert(0, ROOT)
 
 import torch                                                  # noqa: E402
 
 import modeling                                               # noqa: E402  (the reference's import name)
-from stnerf_b200 import CameraPath, PoseRenderer, checkpoint_io   # noqa: E402
-from tests_support import make_cfg                            # noqa: E402  cfg stub with the fields the model reads
-import cases as C                                             # noqa: E402  synthetic rig + checkpoint copy lookup
-from oracle import stnerf_oracle as O                         # noqa: E402  (synthetic scene description only)
+from stnerf_b200 import CameraPath, PoseRenderer, checkpoint_io, synthetic as O   # noqa: E402
+from stnerf_b200.config import make_cfg                       # noqa: E402  cfg stub with the fields the model reads
 
 
 def main():
@@ -43,7 +40,7 @@ def main():
     gt_poses = torch.stack([T for _, T in cams]).numpy()
     gt_Ks = [K.numpy() for K, _ in cams]
     bkgd, frames = O.synthetic_boxes(2)
-    ckpt = C.find_checkpoint("taekwondo")
+    ckpt = checkpoint_io.find_checkpoint("taekwondo")
 
     for session, kw in (("origin", {}), ("shift", dict(shift=[[0, 0, 0], [0, 2, 0], [0, -2, 0]])),
                         ("scale", dict(scale=[1, 0.75, 1.5]))):

@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"),
     sys.path.insert(0, p)
 import torch
 from stnerf_b200 import ops
-from oracle import stnerf_oracle as O     # synthetic camera only
+from stnerf_b200 import synthetic as O
 
 dev = torch.device("cuda", 0)
 peaks = {}

@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"),
     sys.path.insert(0, p)
 import torch
 import bench as B
-from tests_support import make_cfg
+from stnerf_b200.config import make_cfg
 import modeling
 from stnerf_b200 import ops
 

@@ -60,3 +60,31 @@ def campose_to_extrinsic(camposes):
     res[:, 2, :] = camposes[:, 8:12]
     res[:, 3, 3] = 1.0
     return res
+
+
+# ---- checkpoint copies for hosts without the reference tree -----------------------------------------------------------
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CHECKPOINT_DIRS = [os.path.join(_REPO_ROOT, "oracle", "_ref", "ckpt"), "/root/reference/outputs"]
+
+
+def find_checkpoint(scene: str, dirs=None):
+    """Path of the shipped checkpoint of `scene` ('taekwondo' | 'walking'): the git-ignored copy that travels with the
+    repo (`<repo>/oracle/_ref/ckpt/<scene>.pt`) or the reference tree's `outputs/<scene>/layered_rfnr_checkpoint_1.pt`."""
+    for d in (dirs or CHECKPOINT_DIRS):
+        for p in (os.path.join(d, scene + ".pt"), os.path.join(d, scene, "layered_rfnr_checkpoint_1.pt")):
+            if os.path.isfile(p):
+                return p
+    return None
+
+
+def replicate_layers(sd: dict, L: int) -> dict:
+    """configurations with more performers than the checkpoint reuse its nets round-robin."""
+    have = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("spacenets."))
+    out = {k: v for k, v in sd.items() if k.startswith("bkgd_")}
+    for i in range(L):
+        for grp in ("spacenets", "spacenets_fine", "time_deform_nets"):
+            src = "%s.%d." % (grp, i % have)
+            for k, v in sd.items():
+                if k.startswith(src):
+                    out["%s.%d.%s" % (grp, i, k[len(src):])] = v
+    return out

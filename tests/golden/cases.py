@@ -14,13 +14,13 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "st-nerf_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 from oracle import stnerf_oracle as O  # noqa: E402
 
 GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
-CKPT_DIRS = [os.path.join(ROOT, "oracle", "_ref", "ckpt"), "/root/reference/outputs"]
 
 # name -> spec.  weights: "taekwondo" | "walking" (shipped checkpoints) | "synthetic"
 CASES = {
@@ -48,25 +48,7 @@ CASES = {
 }
 
 
-def find_checkpoint(scene: str):
-    for d in CKPT_DIRS:
-        for p in (os.path.join(d, scene + ".pt"), os.path.join(d, scene, "layered_rfnr_checkpoint_1.pt")):
-            if os.path.isfile(p):
-                return p
-    return None
-
-
-def replicate_layers(sd: dict, L: int) -> dict:
-    """configs with more performers than the checkpoint reuse its nets round-robin."""
-    have = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("spacenets."))
-    out = {k: v for k, v in sd.items() if k.startswith("bkgd_")}
-    for i in range(L):
-        for grp in ("spacenets", "spacenets_fine", "time_deform_nets"):
-            src = "%s.%d." % (grp, i % have)
-            for k, v in sd.items():
-                if k.startswith(src):
-                    out["%s.%d.%s" % (grp, i, k[len(src):])] = v
-    return out
+from stnerf_b200.checkpoint_io import find_checkpoint, replicate_layers  # noqa: E402,F401  (shared with bench / examples)
 
 
 def state_dict_for(case: dict):

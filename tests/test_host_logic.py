@@ -114,3 +114,15 @@ def test_unsupported_configs_fail_loudly():
     m = _model(C.CASES["tkd_64_128"])
     with pytest.raises(Exception):
         m(torch.zeros(8, 9), None)            # CPU rays: the product path has no CPU fallback
+
+
+def test_synthetic_generators_in_sync_with_oracle_copy():
+    """stnerf_b200.synthetic (bench / examples inputs) and the oracle-side copy used by the tests must agree."""
+    from stnerf_b200 import synthetic as S
+    b1, f1 = S.synthetic_boxes(3); b2, f2 = O.synthetic_boxes(3)
+    assert torch.equal(b1, b2) and torch.equal(f1, f2)
+    for v in (0, 5):
+        K1, T1 = S.synthetic_camera(v, 16, 1080, 1920); K2, T2 = O.synthetic_camera(v, 16, 1080, 1920)
+        assert torch.equal(K1, K2) and torch.equal(T1, T2)
+    s1, s2 = S.synthetic_state_dict(1, True, seed=4), O.synthetic_state_dict(1, True, seed=4)
+    assert list(s1) == list(s2) and all(torch.equal(s1[k], s2[k]) for k in s1)

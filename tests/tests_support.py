@@ -16,15 +16,7 @@ for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests", 
 import cases as C  # noqa: E402
 
 
-def make_cfg(layer_num, n1, n2, use_space_time, precision="exact", chunk_rays=0):
-    """The cfg fields the model reads (modeling/layered_rfrender.py:23-37) + the two B200 knobs."""
-    M = types.SimpleNamespace(
-        BOARDER_WEIGHT=1e10, SAMPLE_METHOD="BBOX", SAME_SPACENET=False, TKERNEL_INC_RAW=True,
-        POSE_REFINEMENT=False, USE_DIR=True, USE_DEFORM_VIEW=False, USE_DEFORM_TIME=True,
-        USE_SPACE_TIME=use_space_time, BKGD_USE_DEFORM_TIME=False, BKGD_USE_SPACE_TIME=False,
-        DEEP_RGB=False, COARSE_RAY_SAMPLING=n1, FINE_RAY_SAMPLING=n2, B200_PRECISION=precision,
-        B200_CHUNK_RAYS=chunk_rays)
-    return types.SimpleNamespace(MODEL=M, DATASETS=types.SimpleNamespace(LAYER_NUM=layer_num))
+from stnerf_b200.config import make_cfg  # noqa: E402,F401
 
 
 def build_case_model(name, precision="exact", chunk_rays=0, sd=None):
