@@ -54,4 +54,4 @@ def test_tc_exact_vs_fp32_random_shapes(seed):
             ctx = "%s (L=%d n1=%d n2=%d N=%d)" % (k, L, n1, n2, n_rays)
             assert err.max() < 0.1, "garbage: max %.2e %s" % (err.max(), ctx)
             assert (err > 2e-3).mean() <= 0.01 + 2.0 / len(err), "too many rays off: %.4f %s" % ((err > 2e-3).mean(), ctx)
-            assert np.median(err) < 2e-5 and err.mean() < 2e-4, (ctx, np.median(err), err.mean())
+            assert np.median(err) < 1e-4 and err.mean() < 5e-4, (ctx, np.median(err), err.mean())
