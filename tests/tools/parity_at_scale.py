@@ -2,7 +2,7 @@
 """Parity of the GPU path vs the CPU oracle on a larger ray set (default 16384 rays of view 3, 64+128, taekwondo
 checkpoint, injected uniforms).  Test-infrastructure script (imports the oracle); prints one JSON line."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
     sys.path.insert(0, p)
 import numpy as np, torch
