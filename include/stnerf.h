@@ -156,6 +156,15 @@ int stnerf_spacenet(stnerf_handle h, int layer, int fine, const float* pos, cons
 int stnerf_motionnet(stnerf_handle h, int layer, const float* xyzt, int64_t P, int lerp_mode, float* flow,
                      void* stream);
 
+/* Packed-weight image (cache next to the checkpoint; replaces re-running the state_dict -> MMA-layout packing that follows
+ * render/layered_neural_renderer.py:109-117 `torch.load` + `load_state_dict`).  `export` writes every loaded network's
+ * device images (fp32 SIMT layout, fp16 hi/lo tensor-core stream, fp32 bias/head block) into a HOST buffer; with
+ * `host_buf == NULL` it only reports the size.  `import` validates the image against the context (layer count, per-layer
+ * time inputs, sizes) before touching any network and restores the weights without re-packing.  Byte-for-byte the same
+ * device state as `stnerf_load_*` on the original tensors, so renders are bit-identical.                                   */
+int stnerf_weights_export(stnerf_handle h, void* host_buf, size_t capacity, size_t* bytes_needed);
+int stnerf_weights_import(stnerf_handle h, const void* host_buf, size_t bytes);
+
 /* Tensor-core plumbing self-test: one 128x128x64 fp16 UMMA through the library's descriptors, swizzled layout, bulk
  * copy and TMEM load; writes max |D - host reference| (expected < 1e-3).                                     */
 int stnerf_selftest_umma(float* max_err_host);

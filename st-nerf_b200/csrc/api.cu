@@ -195,6 +195,33 @@ int stnerf_reserve(stnerf_handle c, int n1, int n2) {
 }
 size_t stnerf_workspace_bytes(stnerf_handle c) { return c ? c->ws_bytes : 0; }
 
+// fp32 (SIMT) device image of a SpaceNet: [w_i^T | b_i] x 7, w_sigma, w_rgbh^T, b_rgbh, w_rgbo; the scalar biases live in SpaceNetW
+static size_t bind_spacenet(SpaceNetDev& N, bool use_time) {
+  const int krgb = HID + PE_DIR + (use_time ? PE_TIME : 0);
+  const int Ks[7] = {PE_POS, HID, HID, HID, HID + PE_POS, HID, HID};
+  size_t cur = 0;
+  for (int i = 0; i < 7; ++i) {
+    N.w.w[i] = N.blob + cur; cur += (size_t)HID * Ks[i];
+    N.w.b[i] = N.blob + cur; cur += HID;
+  }
+  N.w.w_sigma = N.blob + cur; cur += HID;
+  N.w.w_rgbh = N.blob + cur; cur += (size_t)HEAD * krgb;
+  N.w.b_rgbh = N.blob + cur; cur += HEAD;
+  N.w.w_rgbo = N.blob + cur; cur += 3 * HEAD;
+  N.w.use_time = use_time ? 1 : 0;
+  return cur;
+}
+static size_t bind_motionnet(MotionNetDev& N) {
+  size_t cur = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int K = i == 0 ? PE_MOTION : HEAD;
+    N.w.w[i] = N.blob + cur; cur += (size_t)HEAD * K;
+    N.w.b[i] = N.blob + cur; cur += HEAD;
+  }
+  N.w.w_out = N.blob + cur; cur += 3 * HEAD;
+  return cur;
+}
+
 int stnerf_load_spacenet(stnerf_handle c, int layer, int fine, const float* blob, size_t n) {
   if (!c || !blob || layer < 0 || layer >= c->l || (fine != 0 && fine != 1)) return STNERF_EINVAL;
   const bool use_time = (n == (size_t)SPACENET_FLOATS_TIME);
@@ -204,35 +231,26 @@ int stnerf_load_spacenet(stnerf_handle c, int layer, int fine, const float* blob
   // walk the blob in state_dict order
   const float* p = blob;
   std::vector<float> host;
-  size_t off_w[7], off_b[7];
   const int Ks[7] = {PE_POS, HID, HID, HID, HID + PE_POS, HID, HID};
   for (int i = 0; i < 7; ++i) {
-    off_w[i] = host.size();
     transpose_into(host, p, HID, Ks[i]);
     p += (size_t)HID * Ks[i];
-    off_b[i] = host.size();
     host.insert(host.end(), p, p + HID);
     p += HID;
   }
-  const size_t off_ws = host.size();
   host.insert(host.end(), p, p + HID); p += HID;
   const float b_sigma = *p++;
-  const size_t off_wh = host.size();
   transpose_into(host, p, HEAD, krgb); p += (size_t)HEAD * krgb;
-  const size_t off_bh = host.size();
   host.insert(host.end(), p, p + HEAD); p += HEAD;
-  const size_t off_wo = host.size();
   host.insert(host.end(), p, p + 3 * HEAD); p += 3 * HEAD;
   const float b_o[3] = {p[0], p[1], p[2]};
   SpaceNetDev& N = c->space[fine][layer];
+  N.loaded = false;
   int rc = upload(&N.blob, host);
   if (rc) return rc;
-  for (int i = 0; i < 7; ++i) { N.w.w[i] = N.blob + off_w[i]; N.w.b[i] = N.blob + off_b[i]; }
-  N.w.w_sigma = N.blob + off_ws; N.w.b_sigma = b_sigma;
-  N.w.w_rgbh = N.blob + off_wh; N.w.b_rgbh = N.blob + off_bh;
-  N.w.w_rgbo = N.blob + off_wo;
+  if (bind_spacenet(N, use_time) != host.size()) return STNERF_EINVAL;
+  N.w.b_sigma = b_sigma;
   for (int a = 0; a < 3; ++a) N.w.b_rgbo[a] = b_o[a];
-  N.w.use_time = use_time ? 1 : 0;
   rc = tc_pack_spacenet(N.tc, blob, use_time);
   if (rc) return rc;
   N.loaded = true;
@@ -243,25 +261,142 @@ int stnerf_load_motionnet(stnerf_handle c, int layer, const float* blob, size_t 
   if (!c || !blob || layer < 1 || layer >= c->l || n != (size_t)MOTIONNET_FLOATS) return STNERF_EINVAL;
   const float* p = blob;
   std::vector<float> host;
-  size_t off_w[5], off_b[5];
   for (int i = 0; i < 5; ++i) {
     const int K = i == 0 ? PE_MOTION : HEAD;
-    off_w[i] = host.size();
     transpose_into(host, p, HEAD, K); p += (size_t)HEAD * K;
-    off_b[i] = host.size();
     host.insert(host.end(), p, p + HEAD); p += HEAD;
   }
-  const size_t off_wo = host.size();
   host.insert(host.end(), p, p + 3 * HEAD); p += 3 * HEAD;
   MotionNetDev& N = c->motion[layer];
+  N.loaded = false;
   int rc = upload(&N.blob, host);
   if (rc) return rc;
-  for (int i = 0; i < 5; ++i) { N.w.w[i] = N.blob + off_w[i]; N.w.b[i] = N.blob + off_b[i]; }
-  N.w.w_out = N.blob + off_wo;
+  if (bind_motionnet(N) != host.size()) return STNERF_EINVAL;
   for (int a = 0; a < 3; ++a) N.w.b_out[a] = p[a];
   rc = tc_pack_motionnet(N.tc, blob);
   if (rc) return rc;
   N.loaded = true;
+  return STNERF_OK;
+}
+
+// ---- packed-weight image: every loaded network's device buffers, as they are, behind a small header ----
+namespace {
+constexpr char PACK_MAGIC[8] = {'S', 'T', 'N', 'B', '2', '0', '0', 'W'};
+constexpr uint32_t PACK_VERSION = 1;
+struct PackHeader { char magic[8]; uint32_t version, n_layers, n_records, reserved; };
+struct PackRec { uint32_t kind, fine, layer, use_time; uint64_t simt_floats, stream_bytes, aux_floats, tail_floats; float scalars[4]; uint32_t pad[4]; };
+static size_t rec_payload(const PackRec& r) { return r.simt_floats * 4 + r.stream_bytes + r.aux_floats * 4 + r.tail_floats * 4; }
+static size_t simt_floats_space(bool use_time) { return (size_t)(use_time ? SPACENET_FLOATS_TIME : SPACENET_FLOATS_NOTIME) - 4; }
+static size_t simt_floats_motion() { return (size_t)MOTIONNET_FLOATS - 3; }
+}  // namespace
+
+int stnerf_weights_export(stnerf_handle c, void* buf, size_t capacity, size_t* bytes_needed) {
+  if (!c) return STNERF_EINVAL;
+  std::vector<PackRec> recs;
+  for (int f = 0; f < 2; ++f)
+    for (int i = 0; i < c->l; ++i)
+      if (c->space[f][i].loaded) {
+        const SpaceNetDev& N = c->space[f][i];
+        PackRec r{};
+        r.kind = 0; r.fine = (uint32_t)f; r.layer = (uint32_t)i; r.use_time = (uint32_t)N.w.use_time;
+        r.simt_floats = simt_floats_space(N.w.use_time != 0); r.stream_bytes = tc_stream_bytes(true);
+        r.aux_floats = tc_aux_floats(); r.tail_floats = tc_tail_floats(true);
+        r.scalars[0] = N.w.b_sigma; for (int a = 0; a < 3; ++a) r.scalars[1 + a] = N.w.b_rgbo[a];
+        recs.push_back(r);
+      }
+  for (int i = 1; i < c->l; ++i)
+    if (c->motion[i].loaded) {
+      PackRec r{};
+      r.kind = 1; r.layer = (uint32_t)i;
+      r.simt_floats = simt_floats_motion(); r.stream_bytes = tc_stream_bytes(false);
+      r.aux_floats = tc_aux_floats(); r.tail_floats = 0;
+      for (int a = 0; a < 3; ++a) r.scalars[a] = c->motion[i].w.b_out[a];
+      recs.push_back(r);
+    }
+  if (recs.empty()) return STNERF_ENOWEIGHTS;
+  size_t need = sizeof(PackHeader);
+  for (const PackRec& r : recs) need += sizeof(PackRec) + rec_payload(r);
+  if (bytes_needed) *bytes_needed = need;
+  if (!buf) return STNERF_OK;                         // size query
+  if (capacity < need) return STNERF_EINVAL;
+  uint8_t* p = static_cast<uint8_t*>(buf);
+  PackHeader h{};
+  memcpy(h.magic, PACK_MAGIC, 8); h.version = PACK_VERSION; h.n_layers = (uint32_t)c->l; h.n_records = (uint32_t)recs.size();
+  memcpy(p, &h, sizeof(h)); p += sizeof(h);
+  for (const PackRec& r : recs) {
+    memcpy(p, &r, sizeof(r)); p += sizeof(r);
+    float* simt = reinterpret_cast<float*>(p);
+    uint8_t* stream = p + r.simt_floats * 4;
+    float* aux = reinterpret_cast<float*>(stream + r.stream_bytes);
+    float* tail = aux + r.aux_floats;
+    const float* dev = r.kind == 0 ? c->space[r.fine][r.layer].blob : c->motion[r.layer].blob;
+    const TcNet& tc = r.kind == 0 ? c->space[r.fine][r.layer].tc : c->motion[r.layer].tc;
+    STNERF_CUDA(cudaMemcpy(simt, dev, r.simt_floats * 4, cudaMemcpyDeviceToHost));
+    const int rc = tc_export(tc, r.kind == 0, stream, aux, tail);
+    if (rc) return rc;
+    p += rec_payload(r);
+  }
+  return STNERF_OK;
+}
+
+int stnerf_weights_import(stnerf_handle c, const void* buf, size_t bytes) {
+  if (!c || !buf || bytes < sizeof(PackHeader)) return STNERF_EINVAL;
+  const uint8_t* p = static_cast<const uint8_t*>(buf);
+  const uint8_t* end = p + bytes;
+  PackHeader h;
+  memcpy(&h, p, sizeof(h)); p += sizeof(h);
+  if (memcmp(h.magic, PACK_MAGIC, 8) != 0 || h.version != PACK_VERSION || (int)h.n_layers != c->l) return STNERF_EINVAL;
+  // validate every record against this context before touching any network
+  const uint8_t* q = p;
+  for (uint32_t k = 0; k < h.n_records; ++k) {
+    if ((size_t)(end - q) < sizeof(PackRec)) return STNERF_EINVAL;
+    PackRec r;
+    memcpy(&r, q, sizeof(r)); q += sizeof(r);
+    if (r.kind > 1 || r.fine > 1 || (int)r.layer >= c->l || r.aux_floats != tc_aux_floats()) return STNERF_EINVAL;
+    if (r.kind == 0) {
+      if ((c->desc.space_time[r.layer] != 0) != (r.use_time != 0)) return STNERF_EINVAL;
+      if (r.simt_floats != simt_floats_space(r.use_time != 0) || r.stream_bytes != tc_stream_bytes(true) ||
+          r.tail_floats != tc_tail_floats(true)) return STNERF_EINVAL;
+    } else {
+      if (r.layer < 1 || r.simt_floats != simt_floats_motion() || r.stream_bytes != tc_stream_bytes(false) || r.tail_floats != 0)
+        return STNERF_EINVAL;
+    }
+    if ((size_t)(end - q) < rec_payload(r)) return STNERF_EINVAL;
+    q += rec_payload(r);
+  }
+  if (q != end) return STNERF_EINVAL;
+  for (uint32_t k = 0; k < h.n_records; ++k) {
+    PackRec r;
+    memcpy(&r, p, sizeof(r)); p += sizeof(r);
+    const float* simt = reinterpret_cast<const float*>(p);
+    const uint8_t* stream = p + r.simt_floats * 4;
+    const float* aux = reinterpret_cast<const float*>(stream + r.stream_bytes);
+    const float* tail = aux + r.aux_floats;
+    const std::vector<float> host(simt, simt + r.simt_floats);
+    if (r.kind == 0) {
+      SpaceNetDev& N = c->space[r.fine][r.layer];
+      N.loaded = false;
+      int rc = upload(&N.blob, host);
+      if (rc) return rc;
+      bind_spacenet(N, r.use_time != 0);
+      N.w.b_sigma = r.scalars[0];
+      for (int a = 0; a < 3; ++a) N.w.b_rgbo[a] = r.scalars[1 + a];
+      rc = tc_import(N.tc, true, (int)r.use_time, stream, aux, tail);
+      if (rc) return rc;
+      N.loaded = true;
+    } else {
+      MotionNetDev& N = c->motion[r.layer];
+      N.loaded = false;
+      int rc = upload(&N.blob, host);
+      if (rc) return rc;
+      bind_motionnet(N);
+      for (int a = 0; a < 3; ++a) N.w.b_out[a] = r.scalars[a];
+      rc = tc_import(N.tc, false, 0, stream, aux, nullptr);
+      if (rc) return rc;
+      N.loaded = true;
+    }
+    p += rec_payload(r);
+  }
   return STNERF_OK;
 }
 

@@ -949,6 +949,33 @@ void tc_free(TcNet& net) {
   net.blob = nullptr; net.aux = nullptr; net.w_tail = nullptr; net.blob_bytes = 0;
 }
 
+size_t tc_stream_bytes(bool is_space) { return is_space ? stream_bytes_per_tile<NET_SPACE>() : stream_bytes_per_tile<NET_MOTION>(); }
+size_t tc_aux_floats() { return AUX_FLOATS; }
+size_t tc_tail_floats(bool is_space) { return is_space ? 48 * 128 : 0; }
+
+int tc_export(const TcNet& net, bool is_space, uint8_t* stream_host, float* aux_host, float* tail_host) {
+  if (!net.blob || !net.aux || net.blob_bytes != tc_stream_bytes(is_space) || (is_space && !net.w_tail)) return STNERF_ENOWEIGHTS;
+  STNERF_CUDA(cudaMemcpy(stream_host, net.blob, net.blob_bytes, cudaMemcpyDeviceToHost));
+  STNERF_CUDA(cudaMemcpy(aux_host, net.aux, AUX_FLOATS * sizeof(float), cudaMemcpyDeviceToHost));
+  if (is_space) STNERF_CUDA(cudaMemcpy(tail_host, net.w_tail, tc_tail_floats(true) * sizeof(float), cudaMemcpyDeviceToHost));
+  return STNERF_OK;
+}
+
+int tc_import(TcNet& net, bool is_space, int use_time, const uint8_t* stream_host, const float* aux_host, const float* tail_host) {
+  tc_free(net);
+  net.blob_bytes = tc_stream_bytes(is_space);
+  net.use_time = use_time;
+  STNERF_CUDA(cudaMalloc(&net.blob, net.blob_bytes));
+  STNERF_CUDA(cudaMemcpy(net.blob, stream_host, net.blob_bytes, cudaMemcpyHostToDevice));
+  STNERF_CUDA(cudaMalloc((void**)&net.aux, AUX_FLOATS * sizeof(float)));
+  STNERF_CUDA(cudaMemcpy(net.aux, aux_host, AUX_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+  if (is_space) {
+    STNERF_CUDA(cudaMalloc((void**)&net.w_tail, tc_tail_floats(true) * sizeof(float)));
+    STNERF_CUDA(cudaMemcpy(net.w_tail, tail_host, tc_tail_floats(true) * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return STNERF_OK;
+}
+
 int tc_pack_spacenet(TcNet& net, const float* p, bool use_time) {
   const int krgb = HID + PE_DIR + (use_time ? PE_TIME : 0);
   std::vector<float> aux(AUX_FLOATS, 0.f);

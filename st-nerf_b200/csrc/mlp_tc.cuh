@@ -16,6 +16,12 @@ struct TcNet {
 int tc_pack_spacenet(TcNet& net, const float* blob_host, bool use_time);
 int tc_pack_motionnet(TcNet& net, const float* blob_host);
 void tc_free(TcNet& net);
+// Packed-weight cache: sizes of one network's device images, read-back and restore (no re-packing).
+size_t tc_stream_bytes(bool is_space);
+size_t tc_aux_floats();
+size_t tc_tail_floats(bool is_space);
+int tc_export(const TcNet& net, bool is_space, uint8_t* stream_host, float* aux_host, float* tail_host);
+int tc_import(TcNet& net, bool is_space, int use_time, const uint8_t* stream_host, const float* aux_host, const float* tail_host);
 int tc_selftest(float* max_err_host);   // one 128x128x64 UMMA vs a host reference
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* cbuf, float* raw,
                        float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st);

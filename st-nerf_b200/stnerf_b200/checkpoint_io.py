@@ -3,6 +3,7 @@
     get_iteration_path      data/datasets/utils.py:42-60      newest `layered_rfnr_checkpoint_<iter>.pt` of a directory
     load_checkpoint         render/layered_neural_renderer.py:109-117   `torch.load(...)['model']`, keys missing from the
                             file back-filled from the freshly initialised model, then `load_state_dict`
+    load_checkpoint_cached  the same, with the packed tensor-core weight image cached next to the `.pt` (8f row 3)
     read_intrinsics         data/datasets/utils.py:20-40      `K.txt`: 9 floats per line -> (M,3,3)
     campose_to_extrinsic    data/datasets/utils.py:6-17       `RT_c2w.txt` rows of 12 floats -> (M,4,4)
 """
@@ -40,6 +41,74 @@ def load_checkpoint(model, path, map_location="cpu"):
         model_dict[k] = fresh[k]
     model.load_state_dict(model_dict)
     return missing
+
+
+# ---- packed-weight cache next to the checkpoint -------------------------------------------------------------
+CACHE_MAGIC = b"STNB200C"
+CACHE_SUFFIX = ".b200w"
+
+
+def file_sha256(path, chunk=1 << 20) -> bytes:
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        while True:
+            b = f.read(chunk)
+            if not b:
+                break
+            h.update(b)
+    return h.digest()
+
+
+def read_weight_cache(pt_path, cache_path=None):
+    """The packed image cached for `pt_path`, or None if there is none / it belongs to other file contents / is damaged."""
+    cache_path = cache_path or pt_path + CACHE_SUFFIX
+    if not os.path.isfile(cache_path):
+        return None
+    with open(cache_path, "rb") as f:
+        head = f.read(8 + 32 + 8)
+        if len(head) != 48 or head[:8] != CACHE_MAGIC or head[8:40] != file_sha256(pt_path):
+            return None
+        n = int.from_bytes(head[40:48], "little")
+        image = f.read(n + 1)
+    return image if len(image) == n else None
+
+
+def write_weight_cache(pt_path, image: bytes, cache_path=None):
+    cache_path = cache_path or pt_path + CACHE_SUFFIX
+    tmp = cache_path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(CACHE_MAGIC + file_sha256(pt_path) + len(image).to_bytes(8, "little") + image)
+    os.replace(tmp, cache_path)                      # atomic: concurrent ranks either see the old file or the whole new one
+    return cache_path
+
+
+def load_checkpoint_cached(model, path, device=None, cache_path=None):
+    """`load_checkpoint` with the packed MMA-layout image cached next to the `.pt` (`<path>.b200w`, keyed by the SHA-256 of
+    the checkpoint file).  First call: torch.load + back-fill + pack on the device + write the cache.  Later calls: the
+    image goes straight to the device (no unpickling, no re-packing); a changed `.pt`, a damaged cache or an image the
+    library rejects (other layer configuration / library version) falls back to the first path and rewrites the cache.
+    Returns "cache" or "checkpoint"."""
+    from ._lib import StnerfError
+    image = read_weight_cache(path, cache_path)
+    if image is not None:
+        model.load_packed(image, state_dict_source=lambda: torch.load(path, map_location="cpu")["model"])
+        try:
+            model.export_packed  # noqa: B018  (attribute check: facade models only)
+            model._ensure_native(_device(device))
+            return "cache"
+        except StnerfError:
+            pass
+    load_checkpoint(model, path)
+    try:
+        write_weight_cache(path, model.export_packed(_device(device)), cache_path)
+    except OSError:
+        pass                                         # read-only checkpoint directory: run without the cache
+    return "checkpoint"
+
+
+def _device(device):
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
 
 def read_intrinsics(fn_intrinsic):

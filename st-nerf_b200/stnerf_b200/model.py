@@ -103,6 +103,11 @@ class LayeredRFRender(torch.nn.Module):
 
     # ---- nn.Module-ish surface used by render/layered_neural_renderer.py:105-121 ------------------------------
     def state_dict(self, *a, **k):
+        if getattr(self, "_packed", None) is not None and getattr(self, "_sd_source", None) is not None:
+            src, self._sd_source = self._sd_source, None
+            for k_, v in src().items():                                   # lazily materialise the tensors behind a packed image
+                if k_ in self._sd:
+                    self._sd[k_] = v.detach().to("cpu", torch.float32).clone()
         return OrderedDict((k_, v) for k_, v in self._sd.items())
 
     def load_state_dict(self, sd, strict=True):
@@ -116,7 +121,21 @@ class LayeredRFRender(torch.nn.Module):
                     raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(sd[k].shape), tuple(self._sd[k].shape)))
                 self._sd[k] = sd[k].detach().to("cpu", torch.float32).clone()
         self._uploaded = False
+        self._packed = None
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def load_packed(self, image: bytes, state_dict_source=None):
+        """Take the networks from a packed-weight image (NativeRenderer.export_weights) instead of a state_dict.
+        `state_dict_source`: optional zero-argument callable returning the matching state_dict, used only if someone asks
+        this model for `state_dict()` later (the render path never does)."""
+        self._packed = bytes(image)
+        self._sd_source = state_dict_source
+        self._uploaded = False
+
+    def export_packed(self, device=None) -> bytes:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            return self._ensure_native(dev).export_weights()
 
     def cuda(self, device=None):
         self._device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
@@ -222,7 +241,10 @@ class LayeredRFRender(torch.nn.Module):
                 self._native = NativeRenderer(self.layer_num + 1, st, self.precision, self.chunk_rays)
         if not self._uploaded:
             with torch.cuda.device(device):
-                self._native.load_state_dict(self._sd)
+                if getattr(self, "_packed", None) is not None:
+                    self._native.import_weights(self._packed)
+                else:
+                    self._native.load_state_dict(self._sd)
             self._uploaded = True
         return self._native
 

@@ -66,6 +66,18 @@ class NativeRenderer:
             b = _blob(sd, "time_deform_nets.%d." % (i - 1), MOTIONNET_KEYS)
             L.check(lib.stnerf_load_motionnet(self._h, i, L.ptr(b), b.numel()), "load motionnet %d" % i)
 
+    def export_weights(self) -> bytes:
+        """Packed image of every loaded network (stnerf_weights_export): what `checkpoint_io.load_checkpoint_cached` stores."""
+        need = C.c_size_t(0)
+        L.check(L.lib().stnerf_weights_export(self._h, None, 0, C.byref(need)), "stnerf_weights_export(size)")
+        buf = (C.c_uint8 * need.value)()
+        L.check(L.lib().stnerf_weights_export(self._h, buf, need.value, C.byref(need)), "stnerf_weights_export")
+        return bytes(buf)
+
+    def import_weights(self, image: bytes):
+        buf = (C.c_uint8 * len(image)).from_buffer_copy(image)
+        L.check(L.lib().stnerf_weights_import(self._h, buf, len(image)), "stnerf_weights_import")
+
     def set_precision(self, precision):
         p = L.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
         L.check(L.lib().stnerf_set_precision(self._h, p), "stnerf_set_precision")

@@ -221,3 +221,70 @@ def drive_camera_path(r, sc):
         r.retime_by_key_frames(layer_id, kfl, kf)
     if sc.get("invert"):
         r.invert_poses()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic captured-scene directory: the files FrameLayerDataset / Ray_Dataset_Render read.
+# ---------------------------------------------------------------------------------------------------------------------
+DATASET_SPEC = dict(layer_num=2, frame_num=3, frame_offset=2, scale=0.5, size_test=(96, 54), original=(192, 108), cams=4)
+
+
+def dataset_points(layer_id: int, frame_id: int) -> np.ndarray:
+    """float32-representable points of one layer at one frame (float64 array, as open3d hands them out)."""
+    rng = np.random.RandomState(100 * layer_id + frame_id)
+    if layer_id == 0:
+        p = rng.uniform([-6, -6, -1], [6, 6, 4], size=(257, 3))
+    else:
+        c = np.array([-2.0 + 2.0 * layer_id + 0.1 * frame_id, 0.3 * frame_id, 0.9])
+        p = c + rng.normal(size=(150 + frame_id, 3)) * np.array([0.3, 0.3, 0.5])
+    return p.astype(np.float32).astype(np.float64)
+
+
+def write_ply(path: str, pts: np.ndarray, fmt: str):
+    """fmt: 'ascii' | 'le_f4' | 'le_f8_extra' (binary little endian doubles with colour bytes interleaved) | 'be_f4'."""
+    n = pts.shape[0]
+    with open(path, "wb") as f:
+        if fmt == "ascii":
+            hdr = "ply\nformat ascii 1.0\ncomment synthetic\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nend_header\n" % n
+            f.write(hdr.encode())
+            for p in pts:
+                f.write(("%.9g %.9g %.9g\n" % tuple(np.float32(p))).encode())
+        elif fmt in ("le_f4", "be_f4"):
+            end = "little" if fmt == "le_f4" else "big"
+            hdr = "ply\nformat binary_%s_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement face 0\nproperty list uchar int vertex_indices\nend_header\n" % (end, n)
+            f.write(hdr.encode())
+            f.write(pts.astype("<f4" if fmt == "le_f4" else ">f4").tobytes())
+        elif fmt == "le_f8_extra":
+            hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty uchar red\nproperty double x\nproperty double y\n"
+                   "property uchar green\nproperty double z\nend_header\n" % n)
+            f.write(hdr.encode())
+            dt = np.dtype([("red", "u1"), ("x", "<f8"), ("y", "<f8"), ("green", "u1"), ("z", "<f8")])
+            rec = np.zeros(n, dtype=dt)
+            rec["x"], rec["y"], rec["z"], rec["red"], rec["green"] = pts[:, 0], pts[:, 1], pts[:, 2], 7, 9
+            f.write(rec.tobytes())
+        else:
+            raise ValueError(fmt)
+
+
+def write_synthetic_dataset(root: str, with_image: bool = True):
+    sp = DATASET_SPEC
+    os.makedirs(os.path.join(root, "pose"), exist_ok=True)
+    os.makedirs(os.path.join(root, "background"), exist_ok=True)
+    Ks, Ts = [], []
+    for v in range(sp["cams"]):
+        K, T = O.synthetic_camera(v, sp["cams"], sp["original"][1], sp["original"][0])
+        Ks.append(np.asarray(K, dtype=np.float64).reshape(-1)); Ts.append(np.asarray(T, dtype=np.float64)[:3].reshape(-1))
+    np.savetxt(os.path.join(root, "pose", "K.txt"), np.stack(Ks), fmt="%.10g")
+    np.savetxt(os.path.join(root, "pose", "RT_c2w.txt"), np.stack(Ts), fmt="%.10g")
+    write_ply(os.path.join(root, "background", "0.ply"), dataset_points(0, 0), "le_f8_extra")
+    fmts = {1: "ascii", 2: "le_f4"}
+    for frame_id in range(1 + sp["frame_offset"], sp["frame_offset"] + sp["frame_num"] + 1):
+        d = os.path.join(root, "frame%d" % frame_id, "pointclouds")
+        os.makedirs(d, exist_ok=True)
+        for layer_id in (1, 2):
+            write_ply(os.path.join(d, "%d.ply" % layer_id), dataset_points(layer_id, frame_id),
+                      "be_f4" if (layer_id == 2 and frame_id % 2 == 0) else fmts[layer_id])
+        if with_image:
+            from PIL import Image
+            os.makedirs(os.path.join(root, "frame%d" % frame_id, "images"), exist_ok=True)
+            Image.new("RGB", sp["original"], (10, 20, 30)).save(os.path.join(root, "frame%d" % frame_id, "images", "000.png"))

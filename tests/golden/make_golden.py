@@ -166,15 +166,65 @@ def run_camera_path():
     print("camera_path.npz: %d arrays" % len(out))
 
 
+def run_dataset():
+    """FrameLayerDataset (data/datasets/frame_dataset.py:94-247) executed unmodified on the synthetic scene directory of
+    cases.write_synthetic_dataset.  `open3d` is not installed: a stub module hands the reference the same point arrays the
+    PLY files were written from (the PLY reader itself is tested against those arrays in tests/test_scene_data.py).
+    `data/__init__` is bypassed (it pulls the training loaders); only data.datasets.{utils,frame_dataset} are imported."""
+    import tempfile, types, importlib
+    sp = C.DATASET_SPEC
+    root = tempfile.mkdtemp(prefix="stnerf_ds_")
+    C.write_synthetic_dataset(root)
+
+    class _Cloud:
+        def __init__(self, pts): self.points = pts
+    o3d = types.ModuleType("open3d"); o3d.io = types.SimpleNamespace()
+    def read_point_cloud(path):
+        layer_id = int(os.path.basename(path).split(".")[0])
+        parent = os.path.basename(os.path.dirname(os.path.dirname(path)))
+        frame_id = int(parent[len("frame"):]) if parent.startswith("frame") else 0
+        return _Cloud(C.dataset_points(layer_id, frame_id))
+    o3d.io.read_point_cloud = read_point_cloud
+    sys.modules["open3d"] = o3d
+    R.modules()                                  # puts the reference on sys.path (its `utils` package must resolve first)
+    for name, sub in (("data", "data"), ("data.datasets", os.path.join("data", "datasets"))):
+        m = types.ModuleType(name); m.__path__ = [os.path.join(R.REFERENCE_ROOT, sub)]; sys.modules[name] = m
+    fd = importlib.import_module("data.datasets.frame_dataset")
+    out = {}
+    for fixed in ((-1.0, -1.0), (0.5, 20.0)):
+        cfg = types.SimpleNamespace(
+            DATASETS=types.SimpleNamespace(TRAIN=root, FIXED_NEAR=fixed[0], FIXED_FAR=fixed[1], SCALE=sp["scale"], CAMERA_STEPSIZE=1,
+                                           FILE_OFFSET=0, CAMERA_NUM=0, VIEW_MASK=None))
+        tag = "auto" if fixed[0] == -1.0 else "fixed"
+        for layer_id in range(sp["layer_num"] + 1):
+            for frame_id in range(1 + sp["frame_offset"], sp["frame_offset"] + sp["frame_num"] + 1):
+                import contextlib, io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    d = fd.FrameLayerDataset(cfg, None, frame_id, layer_id)
+                k = "%s.l%d.f%d." % (tag, layer_id, frame_id)
+                out[k + "bbox"] = np.asarray(d.bbox); out[k + "center"] = np.asarray(d.center, dtype=np.float64)
+                out[k + "near"] = np.asarray(d.near); out[k + "far"] = np.asarray(d.far)
+                if layer_id == 0 and frame_id == 1 + sp["frame_offset"] and tag == "auto":
+                    out["Ts"], out["Ks"] = np.asarray(d.Ts), np.asarray(d.Ks)
+                    out["original_size"] = np.asarray(d.get_original_size())
+        import shutil
+        shutil.rmtree(os.path.join(root, "bbox_tmp"), ignore_errors=True)
+        shutil.rmtree(os.path.join(root, "near_far_tmp"), ignore_errors=True)
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **out)
+    print("dataset.npz: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference (build container only)"
     torch.set_num_threads(os.cpu_count())
     stash_checkpoints()
-    names = sys.argv[1:] or (list(C.CASES) + ["functions", "camera_path"])
+    names = sys.argv[1:] or (list(C.CASES) + ["functions", "camera_path", "dataset"])
     for nm in names:
         if nm == "functions":
             run_functions()
         elif nm == "camera_path":
             run_camera_path()
+        elif nm == "dataset":
+            run_dataset()
         else:
             run_case(nm)
