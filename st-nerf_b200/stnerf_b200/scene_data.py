@@ -223,7 +223,7 @@ class RenderDataset:
 
     def get_rays_by_pose_and_K(self, T, K, layer_frame_pair, device="cuda"):
         """(rays (H*W, 6 [+ layer_num+1]), labels, bboxes, near_fars) as ray_dataset.py:268-293; the rays are produced on
-        `device` by the native generator (bit-identical to utils/render_helpers.py:42-126)."""
+        `device` by the native generator (within 2e-6 of utils/render_helpers.py:42-126, tests/test_gpu_stages.py)."""
         from . import ops
         ids = self.frame_ids(layer_frame_pair) if self.use_time else None
         rays = ops.generate_rays(torch.as_tensor(K, dtype=torch.float32), torch.as_tensor(np.asarray(T), dtype=torch.float32),

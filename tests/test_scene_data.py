@@ -110,7 +110,7 @@ def test_render_dataset_missing_cloud(tmp_path):
 
 @pytest.mark.gpu
 def test_dataset_rays_and_render(scene_dir):
-    """Rays for a dataset pose come from the native generator (bit-equal to the oracle's generate_rays) and drive the
+    """Rays for a dataset pose come from the native generator (within 2e-6 of the oracle's generate_rays) and drive the
     model built from the dataset's boxes."""
     from oracle import stnerf_oracle as O
     from stnerf_b200.config import make_cfg
@@ -121,7 +121,7 @@ def test_dataset_rays_and_render(scene_dir):
     rays, labels, bboxes, nf = ds.get_rays_by_pose_and_K(ds.poses[1], ds.Ks[1], pair)
     ref = O.generate_rays(ds.Ks[1], ds.poses[1], ds.height, ds.width)
     assert rays.shape == (ds.height * ds.width, 9)
-    assert torch.equal(rays[:, :6].cpu(), ref) and rays[0, 6:].tolist() == [3.0, 3.0, 4.0]
+    assert float((rays[:, :6].cpu() - ref).abs().max()) <= 2e-6 and rays[0, 6:].tolist() == [3.0, 3.0, 4.0]   # same bar as test_gpu_stages
     m = modeling.build_layered_model(make_cfg(2, 16, 16, True, "exact"))
     m.load_state_dict(O.synthetic_state_dict(2, True, seed=3))
     ds.apply_to(m)
