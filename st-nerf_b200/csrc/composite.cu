@@ -76,21 +76,22 @@ __device__ __forceinline__ bool warp_is_ascending(const float* a, int n, int lan
   return __all_sync(FULL, ok);
 }
 
-// gen_weight + VolumeRenderer.forward over `count` samples addressed through `at(j)` (position in the
-// per-warp arrays).  All lanes return the reduced color/depth/acc.  If w_out != null, w_out[j] = weight.
-template <typename At>
-__device__ __forceinline__ void composite_run(int count, At at, const float* s_t, const float* s_sig, const float* s_r,
-                                              const float* s_g, const float* s_b, float boarder, float near_cut,
-                                              bool use_near_cut, float* w_out, int lane, float out[5]) {
+// gen_weight + VolumeRenderer.forward over `count` samples: sample j lives at position `at(j)` of the per-warp depth /
+// density arrays and its colour is `rgb_at(j)` (already through the sigmoid).  All lanes return the reduced
+// color/depth/acc.  If w_out != null, w_out[j] = weight.
+template <typename At, typename Rgb>
+__device__ __forceinline__ void composite_run(int count, At at, Rgb rgb_at, const float* s_t, const float* s_sig, float boarder,
+                                              float near_cut, bool use_near_cut, float* w_out, int lane, float out[5]) {
   float carry = 1.0f;                      // cumprod of [1, 1-alpha+1e-10, ...][:-1]  (render_layer.py:15)
   float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
   for (int base = 0; base < count; base += 32) {
     const int j = base + lane;
     const bool valid = j < count;
     float f = 1.0f, alpha = 0.0f, tj = 0.0f;
-    int pj = 0;
+    float3 c = make_float3(0.f, 0.f, 0.f);
     if (valid) {
-      pj = at(j);
+      c = rgb_at(j);                                                               // global load issued first
+      const int pj = at(j);
       tj = s_t[pj];
       const float delta = (j == count - 1) ? boarder : (s_t[at(j + 1)] - tj);     // render_layer.py:37-40
       float sg = s_sig[pj];
@@ -107,9 +108,9 @@ __device__ __forceinline__ void composite_run(int count, At at, const float* s_t
     if (valid) {
       const float w = alpha * T;
       if (w_out) w_out[j] = w;
-      cr += s_r[pj] * w;                                                           // render_layer.py:45
-      cg += s_g[pj] * w;
-      cb += s_b[pj] * w;
+      cr += c.x * w;                                                               // render_layer.py:45
+      cg += c.y * w;
+      cb += c.z * w;
       cd += w * tj;                                                                // :46
       ca += w;                                                                     // :47
     }
@@ -161,8 +162,12 @@ __device__ __forceinline__ void sample_pdf_ray(const float* s_t, const float* s_
 // ---------------------------------------------------------------------------------------------------------
 // K5 / K6: one pass (coarse or fine) of per-layer + merged compositing for a chunk of rays.
 // ---------------------------------------------------------------------------------------------------------
+// Per warp in shared memory: depth and (masked) density of every gathered sample, the coarse weights / cdf while
+// resampling, and one scratch area shared by the resampling sort and the merge order.  Colours are NOT staged: they
+// are read straight from the network output (coalesced in the per-layer pass, gathered through L1/L2 in the merged pass),
+// which keeps the footprint at 8-10 bytes per sample and ~32 warps resident per SM.
 struct PassSmem {
-  int per_warp_floats, off_sig, off_r, off_g, off_b, off_w, off_cdf, off_sort, sort_floats;
+  int per_warp_floats, off_sig, off_w, off_cdf, off_sort, sort_floats;
 };
 
 __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -170,12 +175,11 @@ __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<=
 static PassSmem pass_layout(int l, int S, int n2) {
   PassSmem L;
   const int tot = l * S;
-  L.off_sig = tot; L.off_r = 2 * tot; L.off_g = 3 * tot; L.off_b = 4 * tot;
-  L.off_w = 5 * tot;
-  L.off_cdf = L.off_w + S;
-  L.off_sort = L.off_cdf + S;
-  L.off_sort = (L.off_sort + 1) & ~1;       // 8-byte aligned for the uint64 keys
-  int sf = 2 * next_pow2(tot);
+  L.off_sig = tot;
+  L.off_w = 2 * tot;
+  L.off_cdf = L.off_w + (n2 > 0 ? S : 0);
+  L.off_sort = L.off_cdf + (n2 > 0 ? S : 0);
+  int sf = (tot + 1) / 2;                     // merge order: one uint16 per sample
   if (n2 > 0 && next_pow2(S + n2) > sf) sf = next_pow2(S + n2);
   if (n2 > 0 && S + next_pow2(n2) > sf) sf = S + next_pow2(n2);
   L.sort_floats = sf;
@@ -183,29 +187,32 @@ static PassSmem pass_layout(int l, int S, int n2) {
   return L;
 }
 
+constexpr int ORDER_K_BITS = 9;               // STNERF_MAX_S = 512 samples per list, STNERF_MAX_LAYERS = 8 lists
+static_assert(STNERF_MAX_S <= (1 << ORDER_K_BITS) && STNERF_MAX_LAYERS <= (1 << (16 - ORDER_K_BITS)), "merge order code is 16 bits");
+
 __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scene, int n_layers, const PassSmem L) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* base = smem + (size_t)warp * L.per_warp_floats;
   float* s_t = base;
   float* s_sig = base + L.off_sig;
-  float* s_r = base + L.off_r;
-  float* s_g = base + L.off_g;
-  float* s_b = base + L.off_b;
   float* s_w = base + L.off_w;
   float* s_cdf = base + L.off_cdf;
   float* s_sortf = base + L.off_sort;
-  unsigned long long* s_sort64 = reinterpret_cast<unsigned long long*>(s_sortf);
+  uint16_t* order = reinterpret_cast<uint16_t*>(s_sortf);
 
   const int S = a.S, n2 = a.n2;
   const bool fine = a.fine != 0;
   const float near_p = scene.near_plane, boarder = scene.boarder;
   const bool thr_on = scene.apply_thr != 0;
   const long long plane = 5 * a.n_total;
+  unsigned shown_mask = 1u;
+  for (int i = 1; i < n_layers; ++i) shown_mask |= (scene.shown[i] != 0 ? 1u : 0u) << i;
 
   for (long long r = (long long)blockIdx.x * wpb + warp; r < a.n; r += (long long)gridDim.x * wpb) {
     const long long rg = a.ray_base + r;
     int n_m = 0;                                  // entries gathered for the merged composite
+    unsigned slot_layers = 0;                     // 4 bits per gathered list: which layer it is
     bool all_asc = true;                          // every gathered list is non-decreasing (always true for fine passes)
     for (int i = 0; i < n_layers; ++i) {
       float* oimg = a.out + (size_t)(1 + i) * plane;
@@ -216,16 +223,16 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
         if (lane == 4) oimg[4 * a.n_total + rg] = 0.0f;
         continue;
       }
-      const bool shown = (i == 0) || (scene.shown[i] != 0);
+      const bool shown = (shown_mask >> i) & 1u;
       const int off = n_m;
+      slot_layers |= (unsigned)i << (4 * (n_m / S));
       const float* tp = a.t + i * a.t_layer_stride + r * S;
       const float4* rp = reinterpret_cast<const float4*>(a.raw + i * a.raw_layer_stride) + r * S;
       for (int k = lane; k < S; k += 32) {
         const float tk = tp[k];
-        float sg = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        float sg = 0.f;
         if (shown) {
-          const float4 v = rp[k];
-          sg = v.w; cr = v.x; cg = v.y; cb = v.z;
+          sg = rp[k].w;
           if (!fine) {
             if (i > 0) {
               if (tk < 0.0f) sg = 0.0f;                                         // layered_rfrender.py:414
@@ -244,17 +251,20 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
         }
         s_t[off + k] = tk;
         s_sig[off + k] = sg;
-        s_r[off + k] = sigmoidf_ref(cr);
-        s_g[off + k] = sigmoidf_ref(cg);
-        s_b[off + k] = sigmoidf_ref(cb);
       }
       __syncwarp();
       const bool asc = warp_is_ascending(s_t + off, S, lane);
       all_asc = all_asc && asc;
       float o5[5];
       const bool want_w = (!fine) && n2 > 0;
-      composite_run(S, [off](int j) { return off + j; }, s_t, s_sig, s_r, s_g, s_b, boarder, 0.f, false,
-                    want_w ? s_w : nullptr, lane, o5);
+      // a hidden layer contributes sigmoid(0) colours with zero weight (its network output is never read)
+      composite_run(S, [off](int j) { return off + j; },
+                    [rp, shown](int j) {
+                      if (!shown) return make_float3(0.5f, 0.5f, 0.5f);
+                      const float4 v = __ldg(rp + j);
+                      return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
+                    },
+                    s_t, s_sig, boarder, 0.f, false, want_w ? s_w : nullptr, lane, o5);
       if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
       if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
       if (lane == 4) oimg[4 * a.n_total + rg] = o5[4];
@@ -300,34 +310,48 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
     }
     // ---- merged composite over every hit layer's samples, ordered by (t, cat index)  (:425-448 / :587-606)
     {
-      float o5[5];
+      const int n_lists = n_m / S;
       if (all_asc) {
         // every list is sorted: the stable (t, cat index) order is a rank computation -- position of sample (h,k) =
         // k + #(samples of earlier lists with t' <= t) + #(samples of later lists with t' < t)
-        uint16_t* order = reinterpret_cast<uint16_t*>(s_sortf);
-        const int n_lists = n_m / S;
         for (int e = lane; e < n_m; e += 32) {
-          const int h = e / S;
+          const int h = e / S, k = e - h * S;
           const float key = s_t[e];
-          int pos = e - h * S;
+          int pos = k;
           for (int h2 = 0; h2 < n_lists; ++h2) {
             if (h2 == h) continue;
             pos += (h2 < h) ? upper_bound_s(s_t + h2 * S, S, key) : lower_bound_s(s_t + h2 * S, S, key);
           }
-          order[pos] = (uint16_t)e;
+          order[pos] = (uint16_t)((h << ORDER_K_BITS) | k);
         }
-        __syncwarp();
-        composite_run(n_m, [order](int j) { return (int)order[j]; }, s_t, s_sig, s_r, s_g, s_b, boarder, near_p, fine,
-                      nullptr, lane, o5);
       } else {
-        const int P = next_pow2(n_m);
-        for (int j = lane; j < P; j += 32)
-          s_sort64[j] = (j < n_m) ? (((unsigned long long)float_key(s_t[j]) << 32) | (unsigned)j) : ~0ull;
-        __syncwarp();
-        warp_bitonic_sort(s_sort64, P, lane);
-        composite_run(n_m, [s_sort64](int j) { return (int)(s_sort64[j] & 0xffffffffu); }, s_t, s_sig, s_r, s_g, s_b,
-                      boarder, near_p, fine, nullptr, lane, o5);
+        // some list is out of order (degenerate boxes, NaNs): brute-force stable rank under the total order of float_key.
+        // O(n^2), never taken by well-formed rays.
+        for (int e = lane; e < n_m; e += 32) {
+          const int h = e / S, k = e - h * S;
+          const uint32_t key = float_key(s_t[e]);
+          int pos = 0;
+          for (int e2 = 0; e2 < n_m; ++e2) {
+            const uint32_t k2 = float_key(s_t[e2]);
+            pos += (k2 < key || (k2 == key && e2 < e)) ? 1 : 0;
+          }
+          order[pos] = (uint16_t)((h << ORDER_K_BITS) | k);
+        }
       }
+      __syncwarp();
+      float o5[5];
+      const float* raw = a.raw;
+      const long long rls = a.raw_layer_stride;
+      composite_run(n_m,
+                    [order, S](int j) { const int c = order[j]; return (c >> ORDER_K_BITS) * S + (c & ((1 << ORDER_K_BITS) - 1)); },
+                    [order, S, raw, rls, r, slot_layers, shown_mask](int j) {
+                      const int c = order[j];
+                      const int layer = (slot_layers >> (4 * (c >> ORDER_K_BITS))) & 15u;
+                      if (!((shown_mask >> layer) & 1u)) return make_float3(0.5f, 0.5f, 0.5f);
+                      const float4 v = __ldg(reinterpret_cast<const float4*>(raw + layer * rls) + r * S + (c & ((1 << ORDER_K_BITS) - 1)));
+                      return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
+                    },
+                    s_t, s_sig, boarder, near_p, fine, nullptr, lane, o5);
       float* oimg = a.out;
       if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
       if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
@@ -339,19 +363,20 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
 
 int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_layers, cudaStream_t st) {
   if (a.n <= 0) return STNERF_OK;
+  if (a.S > STNERF_MAX_S || n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
   const PassSmem L = pass_layout(n_layers, a.S, a.fine ? 0 : a.n2);
   const size_t per_warp = (size_t)L.per_warp_floats * sizeof(float);
-  int wpb = (int)((200 * 1024) / per_warp);
-  if (wpb < 1) return STNERF_EINVAL;
-  if (wpb > 8) wpb = 8;
+  // blocks of up to 8 warps, as many blocks per SM as shared memory allows (228 KB per SM, 1 KB reserved per block)
+  int wpb = 8;
+  while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
+  if (per_warp * wpb > 200 * 1024) return STNERF_EINVAL;
   const size_t smem = per_warp * wpb;
-  static size_t configured = 0;
-  if (smem > configured) {
-    STNERF_CUDA(cudaFuncSetAttribute(composite_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  STNERF_CUDA(cudaFuncSetAttribute(composite_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm * wpb > 64) per_sm = 64 / wpb;
+  if (per_sm < 1) per_sm = 1;
   long long blocks = (a.n + wpb - 1) / wpb;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148LL * per_sm * 4) blocks = 148LL * per_sm * 4;
   composite_pass_kernel<<<(int)blocks, wpb * 32, smem, st>>>(a, scene, n_layers, L);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;

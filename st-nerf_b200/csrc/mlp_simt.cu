@@ -292,14 +292,8 @@ motionnet_simt_kernel(PointSrc src, MotionNetW W, const int* __restrict__ lerp_f
 
 int launch_spacenet_simt(const PointSrc& src, const SpaceNetW& w, float* raw, long long /*raw_slot_stride*/,
                          float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    STNERF_CUDA(cudaFuncSetAttribute(spacenet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)simt_smem_bytes()));
-    STNERF_CUDA(cudaFuncSetAttribute(motionnet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)simt_smem_bytes()));
-    configured = true;
-  }
+  // set on every launch: the attribute is per device, and one process may drive several (cost: microseconds)
+  STNERF_CUDA(cudaFuncSetAttribute(spacenet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
   spacenet_simt_kernel<<<num_sms, NT, simt_smem_bytes(), st>>>(src, w, raw, rgb_out, sigma_out);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
@@ -307,14 +301,7 @@ int launch_spacenet_simt(const PointSrc& src, const SpaceNetW& w, float* raw, lo
 
 int launch_motionnet_simt(const PointSrc& src, const MotionNetW& w, const int* lerp_flag_dev, int lerp_force,
                           float* xyz_out, float* flow_out, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    STNERF_CUDA(cudaFuncSetAttribute(spacenet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)simt_smem_bytes()));
-    STNERF_CUDA(cudaFuncSetAttribute(motionnet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)simt_smem_bytes()));
-    configured = true;
-  }
+  STNERF_CUDA(cudaFuncSetAttribute(motionnet_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
   motionnet_simt_kernel<<<num_sms, NT, simt_smem_bytes(), st>>>(src, w, lerp_flag_dev, lerp_force, xyz_out, flow_out);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;

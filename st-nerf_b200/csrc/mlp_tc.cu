@@ -29,6 +29,9 @@ namespace stnerf {
 
 namespace {
 
+#ifndef MOTION_CTAS_PER_SM
+#define MOTION_CTAS_PER_SM 1          // resident CTAs per SM the MotionNet instantiation is compiled for (register budget)
+#endif
 constexpr int TILE_M = 128;
 constexpr int ABLOCK = 16384;                // activation block [128 rows x 64 k] fp16, SWIZZLE_128B
 constexpr int STAGE_BYTES = 16384;           // weight stage   [256 rows x 32 k] fp16, SWIZZLE_64B (N=128 layers use half)
@@ -450,7 +453,7 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
 template <int NET>
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PER_SM : 1) mlp_tc_kernel(const TcParams P) {
   using S = Sched<NET>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -1074,11 +1077,8 @@ int tc_selftest(float* max_err_host) {
 
 template <int NET>
 static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    configured = true;
-  }
+  // per-device attribute, set on every launch (one process may drive several devices; cost: microseconds)
+  STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   mlp_tc_kernel<NET><<<num_sms, NTHREADS, SM_TOTAL, st>>>(P);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
