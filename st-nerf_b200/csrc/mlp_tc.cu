@@ -30,7 +30,7 @@ namespace stnerf {
 namespace {
 
 #ifndef MOTION_CTAS_PER_SM
-#define MOTION_CTAS_PER_SM 1          // resident CTAs per SM the MotionNet instantiation is compiled for (register budget)
+#define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
 constexpr int TILE_M = 128;
 constexpr int ABLOCK = 16384;                // activation block [128 rows x 64 k] fp16, SWIZZLE_128B
@@ -176,17 +176,41 @@ template <> struct Sched<NET_SPACE> {
   __host__ __device__ static constexpr int n_out(int l) { return l == 7 ? 128 : 256; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 4; }
   __host__ __device__ static constexpr int enc_chunks(int l) { return (l == 0 || l == 4) ? 1 : 0; }
+  // CTA shape and shared/tensor-memory map: one CTA per SM, the whole 227 KB and all 512 TMEM columns
+  static constexpr int N_THREADS = NTHREADS, EPI_W0 = EPI_WARP0, CTAS_PER_SM = 1;
+  static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
+  static constexpr int tmem_cols = 512, d_stride = 256;
+  static constexpr bool ENC_ALIASES_ACT = false;
 };
 template <> struct Sched<NET_MOTION> {
   static constexpr int N_LAYERS = 5;
-  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * ABLOCK;
   static constexpr int LO_STRIDE = 2 * ABLOCK;
   static constexpr int ENC_LO_STRIDE = 2 * ABLOCK;
   static constexpr int ENC_LAST_USE = 0;
   __host__ __device__ static constexpr int n_out(int) { return 128; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 2; }
   __host__ __device__ static constexpr int enc_chunks(int l) { return l == 0 ? 2 : 0; }
+#if MOTION_CTAS_PER_SM == 2
+  // Two CTAs per SM.  A MotionNet tile is a serial chain (5 layers of N=128: two 64-column chunks per layer leave nothing to
+  // pipeline inside a tile), so the tensor pipe idles while the epilogue warps work and vice versa; a second resident CTA
+  // fills those gaps.  Budget per CTA: 100 KB of shared memory (the encoding shares the activation blocks -- it is
+  // written after the last layer's MMAs have retired -- and the N=128 weight stages are 8 KB), 256 TMEM columns
+  // (2 x 128 accumulators), 10 warps (no spare warps) so that 2 x 320 threads leave 96 registers per thread.
+  static constexpr int act_base = SM_ACT, enc_base = SM_ACT;
+  static constexpr int N_THREADS = 320, EPI_W0 = 2, CTAS_PER_SM = 2;
+  static constexpr int ring_base = 4 * ABLOCK, stage_bytes = 8192, misc_base = ring_base + NSTAGE * stage_bytes,
+                       smem_total = misc_base + MISC_PART + 2048;
+  static constexpr int tmem_cols = 256, d_stride = 128;
+  static constexpr bool ENC_ALIASES_ACT = true;
+#else
+  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * ABLOCK;
+  static constexpr int N_THREADS = NTHREADS, EPI_W0 = EPI_WARP0, CTAS_PER_SM = 1;
+  static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
+  static constexpr int tmem_cols = 512, d_stride = 256;
+  static constexpr bool ENC_ALIASES_ACT = false;
+#endif
 };
+static_assert(2 * (Sched<NET_MOTION>::smem_total + 1024) <= 233472 || Sched<NET_MOTION>::CTAS_PER_SM == 1, "two MotionNet CTAs per SM");
 
 template <int NET>
 __host__ __device__ constexpr size_t stream_bytes_per_tile() {
@@ -258,12 +282,21 @@ __device__ __forceinline__ Pt fetch_pt(const PointSrc& s, long long p, long long
   return q;
 }
 
-// Full-range sin/cos (Cody-Waite + Payne-Hanek slow path) as ONE out-of-line copy: inlining it at every encoding site
-// made the kernels 150-400 KB of SASS, far beyond the instruction cache.
-__device__ __noinline__ float2 sincos_full(float x) {
-  float s, c;
-  sincosf(x, &s, &c);
-  return make_float2(s, c);
+// Full-range sin/cos (Cody-Waite + Payne-Hanek slow path) out of line: inlining it at every encoding site made the
+// kernels 150-400 KB of SASS, far beyond the instruction cache.  Three / four independent angles per call, so the
+// dependent reduction + polynomial chains of the copies interleave (the epilogue warps are latency-bound here: two warps
+// per scheduler).
+struct SinCos3 { float s0, s1, s2, c0, c1, c2; };
+struct SinCos4 { float s0, s1, s2, s3, c0, c1, c2, c3; };
+__device__ __noinline__ SinCos3 sincos_full3(float x0, float x1, float x2) {
+  SinCos3 r;
+  sincosf(x0, &r.s0, &r.c0); sincosf(x1, &r.s1, &r.c1); sincosf(x2, &r.s2, &r.c2);
+  return r;
+}
+__device__ __noinline__ SinCos4 sincos_full4(float x0, float x1, float x2, float x3) {
+  SinCos4 r;
+  sincosf(x0, &r.s0, &r.c0); sincosf(x1, &r.s1, &r.c1); sincosf(x2, &r.s2, &r.c2); sincosf(x3, &r.s3, &r.c3);
+  return r;
 }
 
 // Write NV fp32 values of one row as fp16 hi (+lo) 16-byte chunks: columns col0 .. col0+NV-1 of an activation block
@@ -303,11 +336,8 @@ __device__ __forceinline__ void encode_space_piece(uint8_t* smem, const Pt& pt, 
   float v[16];
   auto trig = [&](int f, float* dst) {
     const float fr = (float)(1 << f);
-    float sn[3], cs[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { const float2 sc = sincos_full(xs[d] * fr); sn[d] = sc.x; cs[d] = sc.y; }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { dst[d] = sn[d]; dst[3 + d] = cs[d]; }
+    const SinCos3 q = sincos_full3(xs[0] * fr, xs[1] * fr, xs[2] * fr);
+    dst[0] = q.s0; dst[1] = q.s1; dst[2] = q.s2; dst[3] = q.c0; dst[4] = q.c1; dst[5] = q.c2;
   };
   if (piece == 0) {
     float t3[6];
@@ -331,19 +361,19 @@ __device__ __forceinline__ void encode_motion_piece(uint8_t* smem, const Pt& pt,
   const float in4[4] = {pt.x, pt.y, pt.z, pt.tm};
   auto trig = [&](int f, float* dst) {
     const float fr = (float)(1 << f);
+    if (!lerp) {
+      const SinCos4 q = sincos_full4(in4[0] * fr, in4[1] * fr, in4[2] * fr, in4[3] * fr);
+      dst[0] = q.s0; dst[1] = q.s1; dst[2] = q.s2; dst[3] = q.s3; dst[4] = q.c0; dst[5] = q.c1; dst[6] = q.c2; dst[7] = q.c3;
+    } else {     // (1-w)*PE([xyz, floor t]) + w*PE([xyz, floor t + 1]) column by column (motion_net.py:63)
+      const SinCos4 q = sincos_full4(in4[0] * fr, in4[1] * fr, in4[2] * fr, lo_t * fr);
+      const SinCos3 q1 = sincos_full3((lo_t + 1.0f) * fr, 0.f, 0.f);
+      const float s0[4] = {q.s0, q.s1, q.s2, q.s3}, c0[4] = {q.c0, q.c1, q.c2, q.c3};
+      const float s1[4] = {q.s0, q.s1, q.s2, q1.s0}, c1[4] = {q.c0, q.c1, q.c2, q1.c0};
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      float sn, cs;
-      if (!lerp) {
-        const float2 sc = sincos_full(in4[d] * fr);
-        sn = sc.x; cs = sc.y;
-      } else {     // (1-w)*PE([xyz, floor t]) + w*PE([xyz, floor t + 1]) column by column (motion_net.py:63)
-        const float a = d < 3 ? in4[d] : lo_t, b2 = d < 3 ? a : lo_t + 1.0f;
-        const float2 sc0 = sincos_full(a * fr), sc1 = sincos_full(b2 * fr);
-        sn = __fadd_rn(__fmul_rn(omw, sc0.x), __fmul_rn(wgt, sc1.x));
-        cs = __fadd_rn(__fmul_rn(omw, sc0.y), __fmul_rn(wgt, sc1.y));
+      for (int d = 0; d < 4; ++d) {
+        dst[d] = __fadd_rn(__fmul_rn(omw, s0[d]), __fmul_rn(wgt, s1[d]));
+        dst[4 + d] = __fadd_rn(__fmul_rn(omw, c0[d]), __fmul_rn(wgt, c1[d]));
       }
-      dst[d] = sn; dst[4 + d] = cs;
     }
   };
   float v[16];
@@ -453,7 +483,7 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
 template <int NET>
-__global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PER_SM : 1) mlp_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const TcParams P) {
   using S = Sched<NET>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -461,10 +491,10 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
     if (threadIdx.x == 0) printf("stnerf mlp_tc: dynamic shared memory base %u is not 1024-byte aligned\n", sbase);
     __trap();
   }
-  const uint32_t bars = sbase + SM_MISC;
+  const uint32_t bars = sbase + S::misc_base;
   auto BAR = [bars](int i) { return bars + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC + MISC_TMEM);
-  float* s_part = reinterpret_cast<float*>(smem + SM_MISC + MISC_PART);     // [128][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::misc_base + MISC_TMEM);
+  float* s_part = reinterpret_cast<float*>(smem + S::misc_base + MISC_PART);     // [128][4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool exact = P.exact != 0;
@@ -477,7 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), S::tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -498,7 +528,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
               const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
               mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
               mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
-              bulk_g2s(sbase + SM_RING + s * STAGE_BYTES, src, bytes, BAR(BAR_WFULL + s));
+              bulk_g2s(sbase + S::ring_base + s * S::stage_bytes, src, bytes, BAR(BAR_WFULL + s));
               ++cnt;
             }
         }
@@ -515,7 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
           const uint32_t b = g & 1;
           mbar_wait(BAR(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);      // accumulator buffer drained (layer g-2)
           tc_fence_after();
-          const uint32_t d = tmem_base + b * 256;
+          const uint32_t d = tmem_base + b * S::d_stride;
           const uint32_t idesc = idesc_n((uint32_t)S::n_out(l));
           const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
           for (int c = 0; c < nch; ++c) {
@@ -542,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
                 const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
                 mbar_wait(BAR(BAR_WFULL + s), n & 1);
                 tc_fence_after();
-                const uint32_t wsm = sbase + SM_RING + s * STAGE_BYTES;
+                const uint32_t wsm = sbase + S::ring_base + s * S::stage_bytes;
                 // hi stage: D += Ahi*Whi (+ Alo*Whi);  lo stage: D += Ahi*Wlo
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
@@ -562,10 +592,10 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp >= S::EPI_W0) {
     // =============================== encoding + epilogue warps ===============================
-    const int ew = warp - EPI_WARP0;            // 0..7
-    const int q = ew & 3, hh = ew >> 2;         // TMEM lane quarter, column half / encoding half
+    const int ew = warp - S::EPI_W0;            // 0..7
+    const int q = warp & 3, hh = ew >> 2;       // TMEM lane quarter (fixed by the warp id), column half / encoding half
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* bias_all = P.aux + AUX_BIAS;
@@ -579,15 +609,17 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
     // encoding of the first tile
     Pt cur = fetch_pt(P.src, (long long)blockIdx.x * TILE_M + row, n_points);
     float carry[2] = {0.f, 0.f};
-    if (NET == NET_MOTION) {
-      // zero padding of the MotionNet encoding blocks (chunks 5.. of block 1, 6.. of block 0): written once, never touched again
+    // zero padding of the MotionNet encoding blocks (chunks 5.. of block 1, 6.. of block 0): written once when the encoding has
+    // its own blocks, before every tile when it shares them with the activations
+    auto zero_motion_pads = [&]() {
       uint8_t* enc = smem + S::enc_base + hh * ABLOCK;
       for (int c = (hh == 0 ? 48 : 40); c < 64; c += 8) {
         const uint32_t off = sw128_offset(row, c);
         *reinterpret_cast<uint4*>(enc + off) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(enc + S::ENC_LO_STRIDE + off) = make_uint4(0, 0, 0, 0);
       }
-    }
+    };
+    if (NET == NET_MOTION) zero_motion_pads();
     if ((long long)blockIdx.x < n_tiles) {
       encode_piece<NET, 0>(smem, cur, row, hh, exact, lerp, carry);
       encode_piece<NET, 1>(smem, cur, row, hh, exact, lerp, carry);
@@ -606,7 +638,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
         const bool last = (l == S::N_LAYERS - 1);
         const int width = S::n_out(l);
         const float* bias = bias_all + l * 256;
-        const uint32_t dcol = lane_taddr + b * 256;
+        const uint32_t dcol = lane_taddr + b * S::d_stride;
         if (!last) {
           TSTAMP(tw0);
           mbar_wait(BAR(BAR_DFULL + b), (g >> 1) & 1);
@@ -644,13 +676,15 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
             constexpr int L_FETCH = (NET == NET_SPACE) ? 1 : 0;
             constexpr int L_P0 = (NET == NET_SPACE) ? 4 : 1;
             if (l == L_FETCH) nxt = fetch_pt(P.src, nt * TILE_M + row, n_points);
-            if (l == L_P0) encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
-            if (l == L_P0 + 1) encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
-            if (NET == NET_MOTION && l == L_P0 + 2) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
-            if (l == L_P0 + (NET == NET_SPACE ? 1 : 2)) {
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+            if (!S::ENC_ALIASES_ACT) {
+              if (l == L_P0) encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
+              if (l == L_P0 + 1) encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
+              if (NET == NET_MOTION && l == L_P0 + 2) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
+              if (l == L_P0 + (NET == NET_SPACE ? 1 : 2)) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+              }
             }
 #ifdef STNERF_TIMING
             tm.enc += clock64() - te0;
@@ -710,6 +744,17 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
+          if (S::ENC_ALIASES_ACT && have_next) {
+            // The last layer's MMAs have retired (d_full above), so nothing reads the activation blocks any more: the next
+            // tile's encoding goes into them now, and its layer 0 runs while this tile's head is combined and written out.
+            zero_motion_pads();
+            encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
+            encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
+            if (NET == NET_MOTION) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+          }
           // combine the two column halves through shared memory
           if (hh == 1) {
             s_part[row * 4 + 0] = dot3[0]; s_part[row * 4 + 1] = dot3[1]; s_part[row * 4 + 2] = dot3[2];
@@ -756,7 +801,7 @@ __global__ void __launch_bounds__(NTHREADS, (NET == NET_MOTION) ? MOTION_CTAS_PE
   // teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, S::tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1078,8 +1123,11 @@ int tc_selftest(float* max_err_host) {
 template <int NET>
 static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   // per-device attribute, set on every launch (one process may drive several devices; cost: microseconds)
-  STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-  mlp_tc_kernel<NET><<<num_sms, NTHREADS, SM_TOTAL, st>>>(P);
+  using S = Sched<NET>;
+  STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_total));
+  if (S::CTAS_PER_SM > 1)     // ask for the largest shared-memory carveout, or the second CTA does not fit next to the first
+    STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  mlp_tc_kernel<NET><<<num_sms * S::CTAS_PER_SM, S::N_THREADS, S::smem_total, st>>>(P);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
 }
