@@ -40,18 +40,18 @@ __device__ __forceinline__ uint32_t float_key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// In-shared-memory bitonic sort of P (power of two) elements by one warp.
+// In-shared-memory bitonic sort of P (power of two) elements by one warp.  Every lane owns whole compare-exchange pairs
+// (pair m of a stride-j step = elements i and i|j with i = m's bits with a zero inserted at bit log2 j), so no lane idles.
 template <typename T>
 __device__ __forceinline__ void warp_bitonic_sort(T* a, int P, int lane) {
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < P; i += 32) {
-        const int p = i ^ j;
-        if (p > i) {
-          const T x = a[i], y = a[p];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { a[i] = y; a[p] = x; }
-        }
+      for (int m = lane; m < (P >> 1); m += 32) {
+        const int i = ((m & ~(j - 1)) << 1) | (m & (j - 1));
+        const int p = i | j;
+        const T x = a[i], y = a[p];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { a[i] = y; a[p] = x; }
       }
       __syncwarp();
     }
@@ -88,9 +88,7 @@ __device__ __forceinline__ void composite_run(int count, At at, Rgb rgb_at, cons
     const int j = base + lane;
     const bool valid = j < count;
     float f = 1.0f, alpha = 0.0f, tj = 0.0f;
-    float3 c = make_float3(0.f, 0.f, 0.f);
     if (valid) {
-      c = rgb_at(j);                                                               // global load issued first
       const int pj = at(j);
       tj = s_t[pj];
       const float delta = (j == count - 1) ? boarder : (s_t[at(j + 1)] - tj);     // render_layer.py:37-40
@@ -108,11 +106,14 @@ __device__ __forceinline__ void composite_run(int count, At at, Rgb rgb_at, cons
     if (valid) {
       const float w = alpha * T;
       if (w_out) w_out[j] = w;
-      cr += c.x * w;                                                               // render_layer.py:45
-      cg += c.y * w;
-      cb += c.z * w;
-      cd += w * tj;                                                                // :46
-      ca += w;                                                                     // :47
+      if (w != 0.0f) {                     // a zero weight adds exactly +0 to every sum: its colour is neither read nor squashed
+        const float3 c = rgb_at(j);        // (most samples: empty space has sigma <= 0.  Only a NaN colour would differ.)
+        cr += c.x * w;                                                             // render_layer.py:45
+        cg += c.y * w;
+        cb += c.z * w;
+        cd += w * tj;                                                              // :46
+        ca += w;                                                                   // :47
+      }
     }
   }
   out[0] = warp_sum(cr); out[1] = warp_sum(cg); out[2] = warp_sum(cb);
