@@ -168,6 +168,9 @@ int stnerf_weights_import(stnerf_handle h, const void* host_buf, size_t bytes);
 /* Tensor-core plumbing self-test: one 128x128x64 fp16 UMMA through the library's descriptors, swizzled layout, bulk
  * copy and TMEM load; writes max |D - host reference| (expected < 1e-3).                                     */
 int stnerf_selftest_umma(float* max_err_host);
+/* The same through the CTA-pair protocol (`tcgen05.mma.cta_group::2`, M = 256 over the two CTAs of a cluster: remote mbarrier
+ * arrives, multicast commit, paired TMEM allocation): one 256x256x64 product; expected < 1e-3.                 */
+int stnerf_selftest_umma_pair(float* max_err_host);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 uint64_t stnerf_launch_count(void);

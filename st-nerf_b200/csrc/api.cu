@@ -602,6 +602,11 @@ int stnerf_selftest_umma(float* max_err_host) {
   return tc_selftest(max_err_host);
 }
 
+int stnerf_selftest_umma_pair(float* max_err_host) {
+  if (!max_err_host) return STNERF_EINVAL;
+  return tc_selftest_pair(max_err_host);
+}
+
 int stnerf_profile_begin(stnerf_handle c) {
   if (!c) return STNERF_EINVAL;
   if (!c->prof_counts) STNERF_CUDA(cudaHostAlloc((void**)&c->prof_counts, (size_t)PROF_MAX_CHUNKS * 32, cudaHostAllocDefault));

@@ -129,6 +129,60 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster issue ONE MMA of M = 256 from the leader; each CTA keeps its
+// own 128 rows of A and half of the B rows in its shared memory, and its 128 accumulator rows in its tensor memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t rank) {     // shared::cluster address of a peer's copy
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {             // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {    // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  for (uint32_t spin = 0; !mbar_try_wait_cluster(bar, parity); ++spin) {
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // {lo16 = fp16(a), hi16 = fp16(b)}, saturating to +-65504 (fp16 range guard of the split)
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   uint32_t r;
@@ -151,6 +205,7 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 }
 // Instruction descriptor: fp16 A/B (K-major), fp32 D, M = 128 (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_n(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+__host__ __device__ constexpr uint32_t idesc_pair_n(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24); }   // M = 256 over a CTA pair
 
 // byte offset of element (row, col) of a [rows x 64] fp16 block, 128B-swizzled K-major (activations)
 __host__ __device__ inline uint32_t sw128_offset(int row, int col) {
@@ -925,6 +980,80 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// self-test of the CTA-pair protocol: D (256 x 256) = A (256 x 64) * B^T (256 x 64) with ONE cta_group::2 accumulator.
+// CTA r of the cluster holds A rows [128 r, 128 r + 128) and B rows (= output columns) [128 r, 128 r + 128) of every stage;
+// the leader waits for its own bulk copy, for the peer's (relayed by a remote arrive) and for both A tiles, issues the
+// MMAs and commits to the `done` barrier of both CTAs; each CTA reads its 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PAIR_HALF_STAGE = STAGE_BYTES / 2;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_pair_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bstages, float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bars = sbase + ABLOCK + 2 * PAIR_HALF_STAGE;
+  const uint32_t bar_full = bars, bar_peer = bars + 8, bar_a = bars + 16, bar_done = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ABLOCK + 2 * PAIR_HALF_STAGE + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_peer, 1);
+    mbar_init(bar_a, 2);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc_pair(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  for (int c0 = 0; c0 < 64; c0 += 32) {        // this CTA's 128 rows of A through the epilogue's store path (hi only)
+    float v[32];
+    for (int i = 0; i < 32; ++i) v[i] = A[((int)rank * 128 + tid) * 64 + c0 + i];
+    store_row_split<32>(smem, 0, tid, c0, v, false);
+  }
+  // exactly the hand-off of the MLP kernel: generic-proxy stores -> async-proxy fence -> CTA barrier -> one release-arrive
+  // (cluster scope) on the LEADER's barrier; the leader's acquire-wait orders the peer's tile before its MMAs
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_cluster(map_to_cta(bar_a, 0));
+    mbar_expect_tx(bar_full, 2 * PAIR_HALF_STAGE);
+    for (int sub = 0; sub < 2; ++sub)
+      bulk_g2s(sbase + ABLOCK + sub * PAIR_HALF_STAGE, Bstages + (size_t)sub * STAGE_BYTES + (size_t)rank * PAIR_HALF_STAGE,
+               PAIR_HALF_STAGE, bar_full);
+    mbar_wait(bar_full, 0);
+    if (rank == 1) {
+      mbar_arrive_cluster(map_to_cta(bar_peer, 0));               // relay: the peer's half of B has landed
+    } else {
+      mbar_wait_cluster(bar_peer, 0);
+      mbar_wait_cluster(bar_a, 0);
+      tc_fence_after();
+      for (int sub = 0; sub < 2; ++sub)
+        for (int ks = 0; ks < 2; ++ks)
+          umma_f16_pair(tmem_base, make_desc_sw128(sbase + sub * 64 + ks * 32),
+                        make_desc_sw64(sbase + ABLOCK + sub * PAIR_HALF_STAGE + ks * 32), idesc_pair_n(256), (sub | ks) ? 1u : 0u);
+      umma_commit_pair(bar_done);
+    }
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  for (int j = 0; j < 8; ++j) {
+    uint32_t acc[32];
+    tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, acc);
+    tmem_ld_wait(acc);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[((int)rank * 128 + warp * 32 + lane) * 256 + j * 32 + i] = __uint_as_float(acc[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs are done with the accumulator before either frees it
+  if (warp == 0) tmem_dealloc_pair(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host: weight packing
 // ---------------------------------------------------------------------------------------------------------
 // One layer of the stream.  W is (N, K_total) row-major.  A 64-wide k-chunk is described by the 64 source columns it
@@ -1111,6 +1240,46 @@ int tc_selftest(float* max_err_host) {
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
   float worst = 0.f;
   for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 256; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 64; ++k) ref += (double)Af[m * 64 + k] * Bf[n * 64 + k];
+      worst = fmaxf(worst, fabsf((float)ref - D[m * 256 + n]));
+    }
+  *max_err_host = worst;
+  return STNERF_OK;
+}
+
+// The same for the CTA-pair protocol: 256 x 256 x 64.
+int tc_selftest_pair(float* max_err_host) {
+  std::vector<float> Af(256 * 64), Bf(256 * 64);
+  uint32_t s = 777u;
+  auto rnd = [&s]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : Af) v = __half2float(__float2half_rn(rnd()));
+  for (auto& v : Bf) v = __half2float(__float2half_rn(rnd()));
+  std::vector<uint8_t> stages(2 * STAGE_BYTES, 0);
+  for (int sub = 0; sub < 2; ++sub)
+    for (int n = 0; n < 256; ++n)
+      for (int c = 0; c < 32; ++c) {
+        const __half h = __float2half_rn(Bf[n * 64 + sub * 32 + c]);
+        memcpy(stages.data() + sub * STAGE_BYTES + sw64_offset(n, c), &h, 2);
+      }
+  float *dA = nullptr, *dD = nullptr; uint8_t* dB = nullptr;
+  STNERF_CUDA(cudaMalloc((void**)&dA, Af.size() * 4));
+  STNERF_CUDA(cudaMalloc((void**)&dB, stages.size()));
+  STNERF_CUDA(cudaMalloc((void**)&dD, 256 * 256 * 4));
+  STNERF_CUDA(cudaMemset(dD, 0, 256 * 256 * 4));
+  STNERF_CUDA(cudaMemcpy(dA, Af.data(), Af.size() * 4, cudaMemcpyHostToDevice));
+  STNERF_CUDA(cudaMemcpy(dB, stages.data(), stages.size(), cudaMemcpyHostToDevice));
+  const int smem = ABLOCK + 2 * PAIR_HALF_STAGE + 64;
+  STNERF_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_pair_selftest_kernel<<<2, 128, smem>>>(dA, dB, dD);
+  STNERF_LAUNCH_CHECK();
+  STNERF_CUDA(cudaDeviceSynchronize());
+  std::vector<float> D(256 * 256);
+  STNERF_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  float worst = 0.f;
+  for (int m = 0; m < 256; ++m)
     for (int n = 0; n < 256; ++n) {
       double ref = 0;
       for (int k = 0; k < 64; ++k) ref += (double)Af[m * 64 + k] * Bf[n * 64 + k];
