@@ -29,6 +29,9 @@ namespace stnerf {
 
 namespace {
 
+#ifndef SPACE_CTA_PAIR
+#define SPACE_CTA_PAIR 0              // 1: SpaceNet tiles run as CTA pairs sharing one cta_group::2 accumulator (see mlp_tc_kernel)
+#endif
 #ifndef MOTION_CTAS_PER_SM
 #define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
@@ -44,9 +47,10 @@ constexpr int SM_ACT = 0;                    // 8 blocks
 constexpr int SM_ENC = 8 * ABLOCK;           // 2 blocks: hi, lo (SpaceNet).  MotionNet: ACT = blocks 0-3, ENC = blocks 4-7
 constexpr int SM_RING = 10 * ABLOCK;
 constexpr int SM_MISC = SM_RING + NSTAGE * STAGE_BYTES;
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_DFULL = 13, BAR_DEMPTY = 15;
-constexpr int MISC_TMEM = 144;
-constexpr int MISC_PART = 160;               // float[128][4]: head partial sums of column-half 1
+constexpr int MAX_STAGE = 8;                 // ring slots a kernel may use (CTA-pair mode: 8 half-size stages in the same 64 KB)
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 29, BAR_DEMPTY = 31;   // 33 barriers
+constexpr int MISC_TMEM = 272;
+constexpr int MISC_PART = 288;               // float[128][4]: head partial sums of column-half 1
 constexpr int SM_TOTAL = SM_MISC + MISC_PART + 2048;
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
@@ -140,26 +144,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {             // release at cluster scope
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Remote arrive / wait with the DEFAULT semantics (release / acquire at CTA scope), as cutlass::arch::ClusterBarrier does.
+// Asking for `.release.cluster` / `.acquire.cluster` makes ptxas emit MEMBAR.ALL.GPU before every arrive and CCTL.IVALL (a full
+// L1 invalidate) after every successful wait -- measured 1.7x slower on the whole kernel.  What crosses the CTA boundary here is
+// shared memory written through `fence.proxy.async` and tensor memory ordered by tcgen05 fences, neither of which lives in L1.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {    // acquire at cluster scope
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  for (uint32_t spin = 0; !mbar_try_wait_cluster(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
-  }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -472,7 +464,7 @@ struct EpiTiming { long long ld = 0, math = 0, fence = 0, arrive = 0, wait_dfull
 #define TSTAMP(x)
 #endif
 
-template <bool SIGMA>
+template <bool SIGMA, bool PAIR = false>
 __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, int row, const float* __restrict__ bias,
                                                   const float* __restrict__ wdot, uint8_t* blk, int lo_stride, bool exact,
                                                   int lane, uint32_t ready_bar, float dot
@@ -526,7 +518,7 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
   fence_proxy_async();
   __syncwarp();
   TSTAMP(t3);
-  if (lane == 0) mbar_arrive(ready_bar);
+  if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar); else mbar_arrive(ready_bar); }
 #ifdef STNERF_TIMING
   const long long t4 = clock64();
   tm.ld += t1 - t0; tm.math += t2 - t1; tm.fence += t3 - t2; tm.arrive += t4 - t3; tm.n += 1;
@@ -537,9 +529,17 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int NET>
+// PAIR: the two CTAs of a cluster share ONE M = 256 accumulator (`cta_group::2`).  Each CTA still owns a 128-point tile -- its
+// activations, its TMEM rows, its epilogue -- but streams only HALF of every weight stage (the B rows of its half of the
+// output columns); the leader (cluster rank 0) issues the MMAs for both, so per SM the B operand reads and the L2 -> shared
+// weight traffic are halved.  Barriers the leader's MMA warp waits on collect arrivals from both CTAs (remote arrives);
+// `tcgen05.commit` multicasts to the same barrier in both CTAs.
+template <int NET, bool PAIR = false>
 __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const TcParams P) {
   using S = Sched<NET>;
+  static_assert(!PAIR || NET == NET_SPACE, "the CTA-pair protocol is built for the SpaceNet schedule");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) {                    // swizzled operands need a 1024-byte aligned base
@@ -556,38 +556,68 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   const long long n_points = src_num_points(P.src);
   const long long n_tiles = (n_points + TILE_M - 1) / TILE_M;
 
+  constexpr uint32_t N_ARRIVE = PAIR ? 2 * N_EPI_WARPS : N_EPI_WARPS;      // epilogue warps of both CTAs report to the leader
+  // weight ring: a CTA of a pair holds half of every stage, so the same 64 KB give twice the slots -- the extra depth pays
+  // for the relay hop (peer's copy lands -> remote arrive -> leader) on top of the L2 latency
+  constexpr uint32_t NST = PAIR ? 2 * NSTAGE : NSTAGE;
+  constexpr uint32_t STAGE_STRIDE = PAIR ? S::stage_bytes / 2 : S::stage_bytes;
+  static_assert(NST <= MAX_STAGE, "barrier slots");
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(BAR(BAR_AREADY + i), N_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_EPI_WARPS); }
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), 1); mbar_init(BAR(BAR_WPEER + i), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(BAR(BAR_AREADY + i), N_ARRIVE);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_ARRIVE); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), S::tmem_cols);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), S::tmem_cols); else tmem_alloc(smem_u32(tmem_slot), S::tmem_cols); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barrier `i` as the LEADER sees it (what the epilogue warps of either CTA arrive on)
+  auto LBAR = [&](int i) { return PAIR ? map_to_cta(BAR(i), 0) : BAR(i); };
+  // tiles: CTA b takes tiles b, b + grid, ...; the CTAs of a pair run the same number of rounds (the odd one out gets a tile
+  // past the end, whose points are all invalid)
+  auto in_range = [&](long long tile) { return PAIR ? ((tile & ~1LL) < n_tiles) : (tile < n_tiles); };
 
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
         const uint8_t* src = P.wstream;
         for (int l = 0; l < S::N_LAYERS; ++l) {
           const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
           const uint32_t bytes = (uint32_t)S::n_out(l) * 64;
+          const uint32_t mine = PAIR ? bytes / 2 : bytes;     // pair: the rows of this CTA's half of the output columns
           for (int sc = 0; sc < nsub; ++sc)
             for (int term = 0; term < 2; ++term, src += bytes) {
               if (term == 1 && !exact) continue;             // fast mode never touches the lo stages
-              const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
+              const uint32_t s = cnt % NST, n = cnt / NST;
               mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
-              mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
-              bulk_g2s(sbase + S::ring_base + s * S::stage_bytes, src, bytes, BAR(BAR_WFULL + s));
+              mbar_expect_tx(BAR(BAR_WFULL + s), mine);
+              bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, src + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
               ++cnt;
             }
         }
       }
+    }
+  } else if (warp == 1 && PAIR && !leader) {
+    // =============================== peer of a pair: relay "my half of stage s has landed" to the leader ===============
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x)
+        for (int l = 0; l < S::N_LAYERS; ++l) {
+          const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
+          for (int sc = 0; sc < nsub; ++sc)
+            for (int term = 0; term < 2; ++term) {
+              if (term == 1 && !exact) continue;
+              const uint32_t s = cnt % NST, n = cnt / NST;
+              mbar_wait(BAR(BAR_WFULL + s), n & 1);
+              mbar_arrive_cluster(map_to_cta(BAR(BAR_WPEER + s), 0));
+              ++cnt;
+            }
+        }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -595,27 +625,28 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       uint32_t cnt = 0;            // weight stages consumed
       uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
       uint32_t a_uses[5] = {0, 0, 0, 0, 0};
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      auto WAIT = [&](uint32_t bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
+      for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
         for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
           const uint32_t b = g & 1;
-          mbar_wait(BAR(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);      // accumulator buffer drained (layer g-2)
+          WAIT(BAR(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);           // accumulator buffer drained (layer g-2)
           tc_fence_after();
           const uint32_t d = tmem_base + b * S::d_stride;
-          const uint32_t idesc = idesc_n((uint32_t)S::n_out(l));
+          const uint32_t idesc = PAIR ? idesc_pair_n((uint32_t)S::n_out(l)) : idesc_n((uint32_t)S::n_out(l));
           const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
             if (c < nact) {
               a_hi = sbase + S::act_base + c * ABLOCK;
               a_lo = a_hi + S::LO_STRIDE;
-              mbar_wait(BAR(BAR_AREADY + c), a_uses[c] & 1);
+              WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1);
               ++a_uses[c];
             } else {
               const int e = c - nact;
               a_hi = sbase + S::enc_base + e * ABLOCK;
               a_lo = a_hi + S::ENC_LO_STRIDE;
               if (l == 0 && e == 0) {                              // one arrival phase per tile covers the whole encoding
-                mbar_wait(BAR(BAR_AREADY + 4), a_uses[4] & 1);
+                WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
                 ++a_uses[4];
               }
             }
@@ -624,26 +655,30 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
               for (int term = 0; term < 2; ++term) {
                 if (term == 1 && !exact) continue;
-                const uint32_t s = cnt % NSTAGE, n = cnt / NSTAGE;
+                const uint32_t s = cnt % NST, n = cnt / NST;
                 mbar_wait(BAR(BAR_WFULL + s), n & 1);
+                if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);      // ... and the peer's half
                 tc_fence_after();
-                const uint32_t wsm = sbase + S::ring_base + s * S::stage_bytes;
+                const uint32_t wsm = sbase + S::ring_base + s * STAGE_STRIDE;
                 // hi stage: D += Ahi*Whi (+ Alo*Whi);  lo stage: D += Ahi*Wlo
+                auto MMA = [&](uint32_t a_addr, int ks, uint32_t acc) {
+                  if (PAIR) umma_f16_pair(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+                  else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+                };
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                  umma_f16(d, make_desc_sw128(a_hi + a_off + ks * 32), make_desc_sw64(wsm + ks * 32), idesc,
-                           (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
                 if (term == 0 && exact) {
 #pragma unroll
-                  for (int ks = 0; ks < 2; ++ks)
-                    umma_f16(d, make_desc_sw128(a_lo + a_off + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, 1u);
+                  for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
                 }
-                umma_commit(BAR(BAR_WEMPTY + s));                   // ring slot reusable once these MMAs retire
+                if (PAIR) umma_commit_pair(BAR(BAR_WEMPTY + s));    // ring slot (of both CTAs) reusable once these MMAs retire
+                else umma_commit(BAR(BAR_WEMPTY + s));
                 ++cnt;
               }
             }
           }
-          umma_commit(BAR(BAR_DFULL + b));                          // accumulator of layer g complete
+          if (PAIR) umma_commit_pair(BAR(BAR_DFULL + b));           // accumulator of layer g complete (in both CTAs)
+          else umma_commit(BAR(BAR_DFULL + b));
         }
       }
     }
@@ -675,17 +710,19 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       }
     };
     if (NET == NET_MOTION) zero_motion_pads();
-    if ((long long)blockIdx.x < n_tiles) {
+    // arrive on the leader's barrier `i` (this CTA's own barrier outside pair mode)
+    auto ARRIVE = [&](int i) { if (PAIR) mbar_arrive_cluster(LBAR(i)); else mbar_arrive(BAR(i)); };
+    if (in_range((long long)blockIdx.x)) {
       encode_piece<NET, 0>(smem, cur, row, hh, exact, lerp, carry);
       encode_piece<NET, 1>(smem, cur, row, hh, exact, lerp, carry);
       if (NET == NET_MOTION) encode_piece<NET, 2>(smem, cur, row, hh, exact, lerp, carry);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+      if (lane == 0) ARRIVE(BAR_AREADY + 4);
     }
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
       const long long nt = tile + gridDim.x;
-      const bool have_next = nt < n_tiles;
+      const bool have_next = in_range(nt);
       Pt nxt = cur;
       float sig_dot = 0.f;
       for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
@@ -704,16 +741,16 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const int nchunk = width / 64;
           if (NET == NET_SPACE && l == 6) {
             for (int j = 0; j < nchunk; ++j)
-              sig_dot = epi_hidden_chunk<true>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
-                                               S::LO_STRIDE, exact, lane, BAR(BAR_AREADY + j), sig_dot
+              sig_dot = epi_hidden_chunk<true, PAIR>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
+                                                     S::LO_STRIDE, exact, lane, LBAR(BAR_AREADY + j), sig_dot
 #ifdef STNERF_TIMING
                                                , tm
 #endif
               );
           } else {
             for (int j = 0; j < nchunk; ++j)
-              epi_hidden_chunk<false>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, exact,
-                                      lane, BAR(BAR_AREADY + j), 0.f
+              epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, exact,
+                                            lane, LBAR(BAR_AREADY + j), 0.f
 #ifdef STNERF_TIMING
                                       , tm
 #endif
@@ -721,7 +758,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
+          if (lane == 0) ARRIVE(BAR_DEMPTY + b);
           // Idle time until the next accumulator is ready: fetch and encode the NEXT tile's points piece by piece.
           // The encoding buffer is free once the MMAs of layer ENC_LAST_USE are done (observed through d_full above).
           //   SpaceNet : fetch after layer 1, pieces after layers 4 and 5
@@ -738,7 +775,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               if (l == L_P0 + (NET == NET_SPACE ? 1 : 2)) {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+                if (lane == 0) ARRIVE(BAR_AREADY + 4);
               }
             }
 #ifdef STNERF_TIMING
@@ -798,7 +835,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_DEMPTY + b));
+          if (lane == 0) ARRIVE(BAR_DEMPTY + b);
           if (S::ENC_ALIASES_ACT && have_next) {
             // The last layer's MMAs have retired (d_full above), so nothing reads the activation blocks any more: the next
             // tile's encoding goes into them now, and its layer 0 runs while this tile's head is combined and written out.
@@ -808,7 +845,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             if (NET == NET_MOTION) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_AREADY + 4));
+            if (lane == 0) ARRIVE(BAR_AREADY + 4);
           }
           // combine the two column halves through shared memory
           if (hh == 1) {
@@ -856,7 +893,8 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   // teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, S::tmem_cols);
+  if (PAIR) cluster_sync_all();                  // neither CTA leaves (or frees tensor memory) while the other may still touch it
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, S::tmem_cols); else tmem_dealloc(tmem_base, S::tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1293,10 +1331,23 @@ template <int NET>
 static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   // per-device attribute, set on every launch (one process may drive several devices; cost: microseconds)
   using S = Sched<NET>;
-  STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_total));
+  constexpr bool PAIR = (NET == NET_SPACE) && (SPACE_CTA_PAIR != 0);
+  auto kern = mlp_tc_kernel<NET, PAIR>;
+  STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_total));
   if (S::CTAS_PER_SM > 1)     // ask for the largest shared-memory carveout, or the second CTA does not fit next to the first
-    STNERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<NET>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  mlp_tc_kernel<NET><<<num_sms * S::CTAS_PER_SM, S::N_THREADS, S::smem_total, st>>>(P);
+    STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (PAIR) {                 // clusters of two CTAs (one TPC): grid = an even number of CTAs, one per SM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(S::N_THREADS); cfg.dynamicSmemBytes = S::smem_total; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    STNERF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    ++g_launches;
+    return STNERF_OK;
+  }
+  kern<<<num_sms * S::CTAS_PER_SM, S::N_THREADS, S::smem_total, st>>>(P);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
 }

@@ -153,3 +153,15 @@ def test_umma_selftest():
     err = ctypes.c_float(-1.0)
     L.check(L.lib().stnerf_selftest_umma(ctypes.byref(err)), "stnerf_selftest_umma")
     assert 0.0 <= err.value < 1e-3, err.value
+
+
+@pytest.mark.gpu
+def test_umma_pair_selftest():
+    """256x256x64 through ONE cta_group::2 accumulator: a 2-CTA cluster, each CTA holding its 128 rows of A and half of the B
+    rows, remote mbarrier arrives on the leader, multicast commit, paired TMEM allocation (the SPACE_CTA_PAIR protocol)."""
+    import ctypes
+    from stnerf_b200 import _lib as L
+    for _ in range(3):
+        err = ctypes.c_float(-1.0)
+        L.check(L.lib().stnerf_selftest_umma_pair(ctypes.byref(err)), "stnerf_selftest_umma_pair")
+        assert 0.0 <= err.value < 1e-3, err.value
