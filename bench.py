@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- rays/sec of the layered ray-march hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision exact|fp32|fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision exact|mixed|fp32|fast]
 
 Workload (BASELINE.json configs[1]): taekwondo 2-layer scene, 1080p, 16 views, 64 coarse + 128 fine samples.
 A *step* renders one 1080p view (2 073 600 rays; view = step mod 16) through the whole hot path: bbox-clipped
@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="exact", choices=["exact", "fp32", "fast"])
+    ap.add_argument("--precision", default="exact", choices=["exact", "mixed", "fp32", "fast"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -302,7 +302,8 @@ def main():
     bk_pts = float(n_local) * (N1 + N1 + N2) * args.steps
     flops = bk_pts * FLOP_SPACE_BKGD + max(0.0, pts - bk_pts) * FLOP_SPACE_PERF
     ach = flops / (sp["ms"] * 1e-3) / 1e12 if sp["ms"] > 0 else 0.0
-    terms = 3 if args.precision == "exact" else 1
+    # executed MMA terms per algorithmic product: 3 (exact); mixed runs rgb_net.1 (256x128 of the 462 336 MAC/point) in one pass
+    terms = {"exact": 3.0, "mixed": 3.0 - 2.0 * (256 * 128) / 462336.0}.get(args.precision, 1.0)
     traffic, traffic_note = None, None
     try:      # DRAM bytes per point of the same kernel from the committed `ncu --set full` capture, scaled to the mean launch
         cap = json.load(open(os.path.join(ROOT, "profiles", "r01_spacenet_traffic.json")))
@@ -348,7 +349,8 @@ def main():
                   "psnr_db": (99.0 if mse == 0 else float(10.0 * __import__("math").log10(1.0 / mse))),
                   "against": "CPU oracle port (pinned to the reference by tests/golden), identical rays/weights/uniforms"}
 
-    dtype = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate"}[args.precision]
+    dtype = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate",
+             "mixed": "f32 via fp16x3 split products on the density path, single f16 pass on the colour-only layer rgb_net.1 (tcgen05), f32 accumulate"}[args.precision]
     print(json.dumps({"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": dtype,

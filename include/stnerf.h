@@ -45,7 +45,10 @@ enum {
   STNERF_PREC_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores: the bit-closest mode, validation baseline      */
   STNERF_PREC_TC_3XF16 = 1,    /* tcgen05 fp16 3-term split (hi*hi + lo*hi + hi*lo), fp32 accumulate:     */
                                /* ~fp32 products, meets the 1e-3 RGB gate               */
-  STNERF_PREC_TC_F16 = 2       /* tcgen05 single fp16 pass: fastest, does NOT meet the 1e-3 gate          */
+  STNERF_PREC_TC_F16 = 2,      /* tcgen05 single fp16 pass: fastest, does NOT meet the 1e-3 gate          */
+  STNERF_PREC_TC_MIXED = 3     /* TC_3XF16 for everything the density depends on (SpaceNet trunk + sigma head, MotionNet); */
+                               /* single fp16 pass for the colour-only layer rgb_net.1 (spacenet.py:81-86): ~5 % fewer     */
+                               /* MMAs, colour error <= 2.5e-4, resampling untouched -- inside the 1e-3 gate               */
 };
 
 typedef struct stnerf_ctx* stnerf_handle;

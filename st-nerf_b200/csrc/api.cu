@@ -184,7 +184,7 @@ void stnerf_destroy(stnerf_handle c) {
 }
 
 int stnerf_set_precision(stnerf_handle c, int precision) {
-  if (!c || precision < 0 || precision > 2) return STNERF_EINVAL;
+  if (!c || precision < 0 || precision > STNERF_PREC_TC_MIXED) return STNERF_EINVAL;
   c->precision = precision;
   return STNERF_OK;
 }

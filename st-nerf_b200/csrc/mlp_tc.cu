@@ -274,6 +274,7 @@ struct TcParams {
   const float* aux;           // fp32: biases [8][256] | w_sigma[256] | b_sigma | w_out[3][128] | b_out[3]
   const float* cbuf;          // SpaceNet: per-slot rgb_net.1 bias (b1 + W1[:,256:].relu(enc(dir,time))), [slots][128]
   int exact;                  // 1: 3-term split, 0: single fp16 pass
+  int single_last;            // with exact: the LAST GEMM layer (SpaceNet rgb_net.1, colour branch only) runs a single pass
   // outputs
   float* raw;                 // float4 per sample (pipeline mode)
   float* rgb_out;             // explicit mode
@@ -553,6 +554,9 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool exact = P.exact != 0;
+  // 3-term split for layer l?  (mixed mode: everything the density depends on is split, the colour-only layer is not)
+  const bool single_last = P.single_last != 0;
+  auto split = [&](int l) { return exact && !(single_last && l == S::N_LAYERS - 1); };
   const long long n_points = src_num_points(P.src);
   const long long n_tiles = (n_points + TILE_M - 1) / TILE_M;
 
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const uint32_t mine = PAIR ? bytes / 2 : bytes;     // pair: the rows of this CTA's half of the output columns
           for (int sc = 0; sc < nsub; ++sc)
             for (int term = 0; term < 2; ++term, src += bytes) {
-              if (term == 1 && !exact) continue;             // fast mode never touches the lo stages
+              if (term == 1 && !split(l)) continue;          // single-pass layers never touch the lo stages
               const uint32_t s = cnt % NST, n = cnt / NST;
               mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
               mbar_expect_tx(BAR(BAR_WFULL + s), mine);
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
           for (int sc = 0; sc < nsub; ++sc)
             for (int term = 0; term < 2; ++term) {
-              if (term == 1 && !exact) continue;
+              if (term == 1 && !split(l)) continue;
               const uint32_t s = cnt % NST, n = cnt / NST;
               mbar_wait(BAR(BAR_WFULL + s), n & 1);
               mbar_arrive_cluster(map_to_cta(BAR(BAR_WPEER + s), 0));
@@ -654,7 +658,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             for (int sub = 0; sub < 2; ++sub) {
               const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
               for (int term = 0; term < 2; ++term) {
-                if (term == 1 && !exact) continue;
+                if (term == 1 && !split(l)) continue;
                 const uint32_t s = cnt % NST, n = cnt / NST;
                 mbar_wait(BAR(BAR_WFULL + s), n & 1);
                 if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);      // ... and the peer's half
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
                 };
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
-                if (term == 0 && exact) {
+                if (term == 0 && split(l)) {
 #pragma unroll
                   for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
                 }
@@ -742,14 +746,14 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           if (NET == NET_SPACE && l == 6) {
             for (int j = 0; j < nchunk; ++j)
               sig_dot = epi_hidden_chunk<true, PAIR>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
-                                                     S::LO_STRIDE, exact, lane, LBAR(BAR_AREADY + j), sig_dot
+                                                     S::LO_STRIDE, split(l + 1), lane, LBAR(BAR_AREADY + j), sig_dot
 #ifdef STNERF_TIMING
                                                , tm
 #endif
               );
           } else {
             for (int j = 0; j < nchunk; ++j)
-              epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, exact,
+              epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, split(l + 1),
                                             lane, LBAR(BAR_AREADY + j), 0.f
 #ifdef STNERF_TIMING
                                       , tm
@@ -1368,7 +1372,8 @@ int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, 
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux; P.cbuf = cbuf;
-  P.exact = precision == STNERF_PREC_TC_3XF16;
+  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED;
+  P.single_last = precision == STNERF_PREC_TC_MIXED;
   P.raw = raw; P.rgb_out = rgb_out; P.sigma_out = sigma_out; P.lerp_force = 0;
   return launch_tc<NET_SPACE>(P, num_sms, st);
 }
@@ -1379,7 +1384,7 @@ int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW&
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux;
-  P.exact = precision == STNERF_PREC_TC_3XF16;
+  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED;      // the flow feeds positions: always split
   P.xyz_out = xyz_out; P.flow_out = flow_out; P.lerp_flag = lerp_flag_dev; P.lerp_force = lerp_force;
   return launch_tc<NET_MOTION>(P, num_sms, st);
 }

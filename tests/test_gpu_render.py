@@ -47,6 +47,17 @@ def test_render_exact_tc_matches_reference(name):
     _check(name, "exact", RGB_TOL)
 
 
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_render_mixed_tc_matches_reference(name):
+    """`mixed`: 3-term split wherever the density depends on it, one fp16 pass on the colour-only layer rgb_net.1 -- same 1e-3
+    gate on every ray, and the sampling (depths, masks) must be EXACTLY what `exact` produces (the colour branch cannot move a sample)."""
+    _check(name, "mixed", RGB_TOL)
+    a, b = run_case_native(name, precision="exact"), run_case_native(name, precision="mixed")
+    for k in a:
+        if k.endswith("depth") or k.endswith("acc") or k.startswith("ray_mask"):
+            assert np.array_equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("name", ["syn_L2_64_128", "tkd_64_128"])
 def test_render_fast_tc_psnr(name):
     """Single-pass fp16 tensor-core mode: not a parity mode; gate on PSNR vs the reference."""

@@ -34,7 +34,7 @@ with torch.no_grad():
 ref = torch.cat(outs, 0)
 cpu_s = time.time() - t0
 res = {"rays": n, "cpu_seconds": cpu_s, "data": data}
-for prec in ("exact", "fp32", "fast"):
+for prec in ("exact", "mixed", "fp32", "fast"):
     m = modeling.build_layered_model(make_cfg(2, B.N1, B.N2, True, prec)); m.load_state_dict(sd); m.set_bkgd_bbox(bkgd); m.set_bboxes(frames)
     m.inject_uniforms(jit.cuda(), u.cuda())
     with torch.no_grad():
