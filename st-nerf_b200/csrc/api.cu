@@ -151,6 +151,7 @@ uint64_t stnerf_launch_count(void) { return g_launches; }
 
 int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   if (!out || !d || d->n_layers < 2 || d->n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
+  if (d->precision < 0 || d->precision > STNERF_PREC_TC_MIXED || d->chunk_rays < 0) return STNERF_EINVAL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STNERF_ENODEVICE; }
   int dev = 0;

@@ -71,3 +71,14 @@ def test_product_never_imports_oracle():
         assert not bad.search(open(os.path.join(ROOT, rel)).read()), rel
     bench = open(os.path.join(ROOT, "bench.py")).read()
     assert len(re.findall(r"from\s+oracle", bench)) == 1 and "def cpu_reference_rate" in bench
+
+
+def test_precision_enum_matches_python_map():
+    """include/stnerf.h STNERF_PREC_* values == the names the Python side accepts (cfg.MODEL.B200_PRECISION / --precision)."""
+    import re
+    from stnerf_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "stnerf.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"STNERF_PREC_(\w+)\s*=\s*(\d+)", hdr)}
+    assert enum == {"FP32_SIMT": 0, "TC_3XF16": 1, "TC_F16": 2, "TC_MIXED": 3}
+    assert L.PRECISIONS["fp32"] == enum["FP32_SIMT"] and L.PRECISIONS["exact"] == enum["TC_3XF16"]
+    assert L.PRECISIONS["fast"] == enum["TC_F16"] and L.PRECISIONS["mixed"] == enum["TC_MIXED"]
