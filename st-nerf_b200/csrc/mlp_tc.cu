@@ -1,6 +1,7 @@
-// tcgen05 / TMEM evaluation of SpaceNet and MotionNet (precision modes TC_3XF16 "exact" and TC_F16 "fast").
+// tcgen05 / TMEM evaluation of SpaceNet and MotionNet (precision modes TC_3XF16 "exact", TC_MIXED "mixed", TC_F16 "fast").
 //
-// One persistent CTA per SM walks tiles of 128 points.  Per tile the whole network runs on-chip:
+// Persistent CTAs (SpaceNet: one per SM; MotionNet: two per SM, see Sched<NET_MOTION>) walk tiles of 128 points.  Per tile the
+// whole network runs on-chip:
 //   * activations (A operand) live in shared memory as fp16 hi/lo pairs in the canonical 128B-swizzled K-major
 //     UMMA layout ([128 rows x 64 k] blocks); they never leave the SM between layers;
 //   * weights (B operand) are pre-packed on the host into [N out-rows x 32 k] fp16 blocks (N = 256 or 128) that are
@@ -11,14 +12,19 @@
 //     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1, k-chunk by k-chunk;
 //   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which
 //     reproduces fp32 products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate);
+//     mixed mode keeps that everywhere the density depends on and runs the colour-only layer rgb_net.1 in one pass;
 //   * the input encoding of tile i+1 is written while the tensor core works on the late layers of tile i;
 //   * relu(PE(dir) | PE(time)) enters rgb_net.1 as a per-ray fp32 bias computed by head_bias_kernel
 //     (b1 + W1[:,256:] . relu(enc)), so the last GEMM is a clean K=256;
 //   * the 1-wide density head, the 3-wide rgb / flow heads and all biases are fp32 FFMA work in the epilogue.
 //
-// Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue /
+// Warp roles (SpaceNet, 384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue /
 // encoding warps: warp%4 selects the TMEM lane quarter (row = 32*(warp%4) + lane), (warp-4)/4 the column half of
-// every 64-column chunk and the half of the encoding frequencies the thread computes for its row.
+// every 64-column chunk and the half of the encoding frequencies the thread computes for its row.  (MotionNet, 320 threads:
+// the same roles without the two spare warps, epilogue warps 2..9.)
+//
+// Build flags: SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not
+// faster: DESIGN.md 8.1); MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout (A/B reference).
 //
 // Restates modeling/spacenet.py:101-160, modeling/motion_net.py:34-71, utils/dimension_kernel.py:24-33.
 #include <cuda_fp16.h>
