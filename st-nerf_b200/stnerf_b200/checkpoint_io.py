@@ -90,15 +90,16 @@ def load_checkpoint_cached(model, path, device=None, cache_path=None):
     library rejects (other layer configuration / library version) falls back to the first path and rewrites the cache.
     Returns "cache" or "checkpoint"."""
     from ._lib import StnerfError
+    if not (hasattr(model, "load_packed") and hasattr(model, "export_packed")):
+        raise TypeError("load_checkpoint_cached needs a stnerf_b200 model (build_layered_model); got %s" % type(model).__name__)
     image = read_weight_cache(path, cache_path)
     if image is not None:
         model.load_packed(image, state_dict_source=lambda: torch.load(path, map_location="cpu")["model"])
         try:
-            model.export_packed  # noqa: B018  (attribute check: facade models only)
-            model._ensure_native(_device(device))
+            model._ensure_native(_device(device))        # uploads the image; the library validates it against this model
             return "cache"
         except StnerfError:
-            pass
+            pass                                         # other layer configuration / library version: rebuild below
     load_checkpoint(model, path)
     try:
         write_weight_cache(path, model.export_packed(_device(device)), cache_path)
