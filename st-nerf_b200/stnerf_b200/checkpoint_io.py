@@ -92,6 +92,9 @@ def load_checkpoint_cached(model, path, device=None, cache_path=None):
     from ._lib import StnerfError
     if not (hasattr(model, "load_packed") and hasattr(model, "export_packed")):
         raise TypeError("load_checkpoint_cached needs a stnerf_b200 model (build_layered_model); got %s" % type(model).__name__)
+    if not torch.cuda.is_available():                  # nothing to pack on: plain load; rendering will fail loudly later
+        load_checkpoint(model, path)
+        return "checkpoint"
     image = read_weight_cache(path, cache_path)
     if image is not None:
         model.load_packed(image, state_dict_source=lambda: torch.load(path, map_location="cpu")["model"])
