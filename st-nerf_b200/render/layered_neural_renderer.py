@@ -173,6 +173,47 @@ class LayeredNeuralRenderer(CameraPath):
                         self.depths_layer[layer_id].append(depth)
             self.image_num += 1
 
+    # ---- :550-618 (flat folder layout + the layer-2-over-background composite "02") --------------------------------------------
+    def render_path_walking(self, inverse_y_axis=False, density_threshold=0, bkgd_density_threshold=0, auto_save=True):
+        self.images, self.depths = [], []
+        self.images_layer = [[] for _ in range(self.layer_num + 1)]
+        self.depths_layer = [[] for _ in range(self.layer_num + 1)]
+        self.image_num = 0
+
+        def folder(leaf, depth=True):
+            d = os.path.join(self.output_dir, str(leaf))
+            if not os.path.exists(d):
+                os.makedirs(os.path.join(d, "color"))
+                if depth:
+                    os.makedirs(os.path.join(d, "depth"))
+            return d
+
+        frames = self._pose_renderer.render_path(self.poses, self.Ks, self.layer_frame_pairs, density_threshold, bkgd_density_threshold)
+        for color, depth, color_layer, depth_layer in frames:
+            if inverse_y_axis:
+                color, depth = torch.flip(color, [0]), torch.flip(depth, [0])
+                color_layer = [torch.flip(i, [0]) for i in color_layer]
+                depth_layer = [torch.flip(i, [0]) for i in depth_layer]
+            if auto_save:
+                d = folder("mixed")
+                _imwrite(os.path.join(d, "color", "%d.jpg" % self.image_num), color)
+                _imwrite(os.path.join(d, "depth", "%d.png" % self.image_num), depth)
+                self.images.append(color)
+                self.depths.append(depth)
+                for layer_id in range(self.layer_num + 1):
+                    d = folder(layer_id)
+                    _imwrite(os.path.join(d, "color", "%d.jpg" % self.image_num), color_layer[layer_id])
+                    _imwrite(os.path.join(d, "depth", "%d.png" % self.image_num), depth_layer[layer_id])
+                    self.images_layer[layer_id].append(color)
+                    self.depths_layer[layer_id].append(depth)
+                color_hide = color_layer[0].clone()                     # layer 2 pasted over the background where it is nearer (:601-605)
+                index = depth_layer[2] < depth_layer[0]
+                index = torch.cat([index, index, index], dim=2)
+                index = torch.logical_and(index, color_layer[2] != 0)
+                color_hide[index] = color_layer[2][index]
+                _imwrite(os.path.join(folder("02", depth=False), "color", "%d.jpg" % self.image_num), color_hide)
+            self.image_num += 1
+
     # ---- small helpers -----------------------------------------------------------------------------------------------------------
     def save_poses(self, path):
         np.save(path, self.poses)
