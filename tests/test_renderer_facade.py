@@ -97,3 +97,9 @@ def test_render_path_layout_and_pixels(dirs):
     assert float((stage2[0].reshape(r.height, r.width, 3).cpu() - r.images[1]).abs().max()) < 2e-6
     r.save_video()                                                # without imageio: counts the take, leaves the frames
     assert r.save_count == 1
+    # the walking variant: flat folders, every layer written, plus the layer-2-over-background composite "02" (:550-618)
+    r.show_layer(2)
+    r.render_path_walking(auto_save=True)
+    for leaf in ("mixed", "0", "1", "2", "02"):
+        assert sorted(os.listdir(os.path.join(r.output_dir, leaf, "color"))) == ["0.jpg", "1.jpg", "2.jpg"], leaf
+    assert not os.path.exists(os.path.join(r.output_dir, "02", "depth")) and len(r.images) == 3
