@@ -13,7 +13,7 @@
 
 namespace stnerf {
 thread_local char g_cuda_err[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }  // namespace stnerf
 
 using namespace stnerf;
@@ -147,7 +147,7 @@ const char* stnerf_strerror(int code) {
   }
 }
 const char* stnerf_last_cuda_error(void) { return g_cuda_err; }
-uint64_t stnerf_launch_count(void) { return g_launches; }
+uint64_t stnerf_launch_count(void) { return g_launches.load(); }
 
 int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   if (!out || !d || d->n_layers < 2 || d->n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;

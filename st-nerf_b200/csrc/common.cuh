@@ -1,5 +1,6 @@
 // Shared declarations of libstnerf_b200 (device structs, error plumbing, Philox).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -11,7 +12,7 @@ namespace stnerf {
 // error plumbing
 // ---------------------------------------------------------------------------------------------------------
 extern thread_local char g_cuda_err[512];
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;    // kernels launched by this library (contexts may live on several host threads)
 
 #define STNERF_CUDA(expr)                                                                        \
   do {                                                                                           \
