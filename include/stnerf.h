@@ -58,7 +58,7 @@ typedef struct {
   int32_t space_time[STNERF_MAX_LAYERS];         /* net of layer i consumes PE(time) in its rgb head           */
                                                  /* (cfg.MODEL.USE_SPACE_TIME, layered_rfrender.py:62-67)       */
   int32_t precision;                             /* STNERF_PREC_*                                               */
-  int32_t chunk_rays;                            /* rays per internal chunk; 0 = default (65536)                */
+  int32_t chunk_rays;                            /* rays per internal chunk; 0 = default (65536); at most 2^22-1  */
 } stnerf_model_desc;
 
 /* Per-call scene constants: what LayeredRFRender.forward derives in its prologue
@@ -113,6 +113,7 @@ int stnerf_set_scene(stnerf_handle h, const stnerf_scene* scene_host);
  * out:    [2 passes: 0 coarse, 1 fine][l+1 images: 0 mixed, 1+i layer i] planes of 5*n_rays floats each,
  *         a plane = rgb (n_rays,3) | depth (n_rays) | acc (n_rays)   (the tuples of :725-734).
  *         With only_coarse the fine planes are left untouched (the facade aliases them, :721-722).
+ *         The caller's current device must be the one the context was created on (else STNERF_EINVAL).
  * ray_mask: (l, n_rays) uint8, |bin_width| > 1e-5 (layers/RaySamplePoint.py:105).                        */
 int stnerf_render(stnerf_handle h, const float* rays, int64_t n_rays, int ray_stride, int n1, int n2,
                   int only_coarse, const float* jitter, const float* u, uint64_t seed,
@@ -174,6 +175,12 @@ int stnerf_selftest_umma(float* max_err_host);
 /* The same through the CTA-pair protocol (`tcgen05.mma.cta_group::2`, M = 256 over the two CTAs of a cluster: remote mbarrier
  * arrives, multicast commit, paired TMEM allocation): one 256x256x64 product; expected < 1e-3.                 */
 int stnerf_selftest_umma_pair(float* max_err_host);
+
+/* Diagnostic read-back of the sample depths of the LAST chunk rendered by stnerf_render (parity tooling: which depths did
+ * utils/sample_pdf.py:18-63 + the sort of modeling/layered_rfrender.py:462 produce for these rays?).
+ * what = 0: coarse depths of `layer`, (n_rays, n1);  what = 1: fine depths, (n_rays, n1+n2).  dst is a DEVICE buffer of
+ * n_rays*S floats; n_rays must not exceed the rays of that chunk and S must be the sample count of that call.          */
+int stnerf_debug_read_depths(stnerf_handle h, int what, int layer, float* dst, int64_t n_rays, int S, void* stream);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 uint64_t stnerf_launch_count(void);

@@ -45,6 +45,8 @@ struct stnerf_ctx {
   bool have_scene = false;
   // workspace (sized for chunk_rays rays, cap_n1 coarse and cap_s2 total samples)
   int cap_n1 = 0, cap_s2 = 0;
+  long long last_chunk_rays = 0;       // geometry of the most recent chunk (stnerf_debug_read_depths)
+  int last_n1 = 0, last_s2 = 0;
   float *t_coarse = nullptr, *raw_coarse = nullptr, *t_fine = nullptr, *raw_fine = nullptr, *xyz = nullptr;
   float* cbuf = nullptr;       // per-slot rgb_net.1 bias of the SpaceNet being evaluated (tensor-core modes)
   uint8_t* mask_ws = nullptr;
@@ -152,6 +154,8 @@ uint64_t stnerf_launch_count(void) { return g_launches.load(); }
 int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   if (!out || !d || d->n_layers < 2 || d->n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
   if (d->precision < 0 || d->precision > STNERF_PREC_TC_MIXED || d->chunk_rays < 0) return STNERF_EINVAL;
+  // the kernels index samples of a chunk with 32-bit integers: chunk_rays * STNERF_MAX_S must stay below 2^31
+  if ((long long)d->chunk_rays * STNERF_MAX_S >= (1LL << 31)) return STNERF_EINVAL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STNERF_ENODEVICE; }
   int dev = 0;
@@ -501,6 +505,11 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
                   const float* jitter, const float* u, uint64_t seed, float* out, uint8_t* ray_mask, void* stream) {
   if (!c || !rays || !out || n_rays < 0) return STNERF_EINVAL;
   if (!c->have_scene) return STNERF_EINVAL;
+  {                                         // the context's weights and workspace live on the device it was created on
+    int cur = -1;
+    STNERF_CUDA(cudaGetDevice(&cur));
+    if (cur != c->device) return STNERF_EINVAL;
+  }
   if (ray_stride < 6 + (c->scene.shared_frame_id ? 1 : c->l)) return STNERF_EINVAL;   // the reference prints + exit(-1) (:162-163)
   if (n1 < 3 || n1 > STNERF_MAX_N1) return STNERF_EINVAL;
   if (only_coarse) n2 = 0;
@@ -513,6 +522,7 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
   const long long plane = 5 * N;
   for (long long c0 = 0; c0 < N; c0 += R) {
     const long long n = std::min(R, N - c0);
+    c->last_chunk_rays = n; c->last_n1 = n1; c->last_s2 = n2 > 0 ? S2 : 0;
     const float* rch = rays + c0 * ray_stride;
     STNERF_CUDA(cudaMemsetAsync(c->counts, 0, STNERF_MAX_LAYERS * 4, st));
     STNERF_CUDA(cudaMemsetAsync(c->lerp_flags, 0, STNERF_MAX_LAYERS * 4, st));
@@ -589,6 +599,16 @@ int stnerf_render_host(stnerf_handle c, const float* rays_host, int64_t n_rays, 
   STNERF_CUDA(cudaMemcpyAsync(out_host, c->h_out, ob_used, cudaMemcpyDeviceToHost, st));
   if (ray_mask_host) STNERF_CUDA(cudaMemcpyAsync(ray_mask_host, c->h_mask, mb, cudaMemcpyDeviceToHost, st));
   STNERF_CUDA(cudaStreamSynchronize(st));
+  return STNERF_OK;
+}
+
+int stnerf_debug_read_depths(stnerf_handle c, int what, int layer, float* dst, int64_t n_rays, int S, void* stream) {
+  if (!c || !dst || layer < 0 || layer >= c->l || n_rays < 0 || (what != 0 && what != 1)) return STNERF_EINVAL;
+  if (!c->t_coarse || n_rays > c->last_chunk_rays) return STNERF_EINVAL;
+  if (S != (what ? c->last_s2 : c->last_n1)) return STNERF_EINVAL;
+  const long long R = c->chunk_rays;
+  const float* src = what ? c->t_fine + (size_t)layer * R * c->cap_s2 : c->t_coarse + (size_t)layer * R * c->cap_n1;
+  STNERF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n_rays * S * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return STNERF_OK;
 }
 

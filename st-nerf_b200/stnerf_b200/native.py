@@ -24,6 +24,14 @@ def _blob(sd: Dict[str, torch.Tensor], prefix: str, names: Sequence[str]) -> tor
     return torch.cat(parts).contiguous()
 
 
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise L.StnerfError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise L.StnerfError("%s must be float32, got %s" % (name, t.dtype))
+    return t.detach().contiguous()
+
+
 class NativeRenderer:
     """One libstnerf context (one GPU, one set of networks)."""
 
@@ -127,19 +135,34 @@ class NativeRenderer:
     # ---- per-stage entry points that need the networks ------------------------------------------------------
     def spacenet(self, layer: int, fine: bool, pos, dirs, times=None):
         P = pos.shape[0]
-        rgb = torch.empty((P, 3), dtype=torch.float32, device=pos.device)
-        sig = torch.empty((P, 1), dtype=torch.float32, device=pos.device)
-        L.check(L.lib().stnerf_spacenet(self._h, layer, 1 if fine else 0, L.ptr(pos.contiguous()),
-                                        L.ptr(dirs.contiguous()), L.ptr(None if times is None else times.contiguous()),
-                                        P, L.ptr(rgb), L.ptr(sig), L.stream_ptr()), "stnerf_spacenet")
+        # the contiguous fp32 copies stay bound to locals until the call has been enqueued (a temporary would be
+        # released -- and its block reused by the next .contiguous() -- before the kernel runs)
+        pos_c, dirs_c = _dev_f32(pos, "pos"), _dev_f32(dirs, "dirs")
+        times_c = None if times is None else _dev_f32(times, "times")
+        rgb = torch.empty((P, 3), dtype=torch.float32, device=pos_c.device)
+        sig = torch.empty((P, 1), dtype=torch.float32, device=pos_c.device)
+        with torch.cuda.device(pos_c.device):
+            L.check(L.lib().stnerf_spacenet(self._h, layer, 1 if fine else 0, L.ptr(pos_c), L.ptr(dirs_c), L.ptr(times_c),
+                                            P, L.ptr(rgb), L.ptr(sig), L.stream_ptr()), "stnerf_spacenet")
+        del pos_c, dirs_c, times_c
         return rgb, sig
 
     def motionnet(self, layer: int, xyzt, lerp_mode: int = -1):
         P = xyzt.shape[0]
-        flow = torch.empty((P, 3), dtype=torch.float32, device=xyzt.device)
-        L.check(L.lib().stnerf_motionnet(self._h, layer, L.ptr(xyzt.contiguous()), P, lerp_mode, L.ptr(flow),
-                                         L.stream_ptr()), "stnerf_motionnet")
+        xyzt_c = _dev_f32(xyzt, "xyzt")
+        flow = torch.empty((P, 3), dtype=torch.float32, device=xyzt_c.device)
+        with torch.cuda.device(xyzt_c.device):
+            L.check(L.lib().stnerf_motionnet(self._h, layer, L.ptr(xyzt_c), P, lerp_mode, L.ptr(flow), L.stream_ptr()),
+                    "stnerf_motionnet")
+        del xyzt_c
         return flow
+
+    def read_depths(self, fine: bool, layer: int, n_rays: int, S: int) -> torch.Tensor:
+        """Sample depths (n_rays, S) of `layer` from the last chunk rendered (stnerf_debug_read_depths; parity tooling)."""
+        out = torch.empty((n_rays, S), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        L.check(L.lib().stnerf_debug_read_depths(self._h, 1 if fine else 0, int(layer), L.ptr(out), int(n_rays), int(S),
+                                                 L.stream_ptr()), "stnerf_debug_read_depths")
+        return out
 
     def set_ray_ids(self, base: int = 0, width: int = 0, row_stride: int = 0):
         """Philox keys of the rays of subsequent render calls (see include/stnerf.h: stnerf_set_ray_ids)."""

@@ -1,8 +1,21 @@
 """Reference import name `utils` (utils/__init__.py:7-13): boundary helpers + per-stage operators."""
 import torch
 
-from stnerf_b200 import ops
-from .batchify_rays import batchify_ray, layered_batchify_ray, layered_batchify_ray_big
+from stnerf_b200 import _fallthrough, ops
+
+# `utils.<name>` for anything not replaced here (metrics, render_helpers, ...) resolves to the reference tree when one is on
+# sys.path (stnerf_b200/_fallthrough.py); the submodules the demos import by name (`logger`, `vis_density`, `high_dim_dics`,
+# `batchify_rays`) ship here so the import block of demo/taekwondo_demo.py:16-23 works with or without it.
+_fallthrough.extend("utils", __path__)
+
+from .batchify_rays import batchify_ray, layered_batchify_ray, layered_batchify_ray_big  # noqa: E402
+from .vis_density import vis_density  # noqa: E402
+from .high_dim_dics import add_two_dim_dict, add_three_dim_dict  # noqa: E402
+
+try:      # camera helpers of the reference (`lookat`, `getSphericalPosition`: utils/render_helpers.py:5-40), when it is there
+    from .render_helpers import lookat, getSphericalPosition  # noqa: E402,F401
+except ImportError:
+    pass
 
 
 class Trigonometric_kernel:
@@ -62,4 +75,5 @@ def ray_sampling_label_bbox(*a, **k):
 ray_sampling_label_label = ray_sampling_label_bbox
 
 __all__ = ["Trigonometric_kernel", "sample_pdf", "generate_rays", "ray_sampling", "batchify_ray",
-           "layered_batchify_ray", "layered_batchify_ray_big", "ray_sampling_label_bbox", "ray_sampling_label_label"]
+           "layered_batchify_ray", "layered_batchify_ray_big", "ray_sampling_label_bbox", "ray_sampling_label_label",
+           "vis_density", "add_two_dim_dict", "add_three_dim_dict"]

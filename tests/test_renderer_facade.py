@@ -103,3 +103,62 @@ def test_render_path_layout_and_pixels(dirs):
     for leaf in ("mixed", "0", "1", "2", "02"):
         assert sorted(os.listdir(os.path.join(r.output_dir, leaf, "color"))) == ["0.jpg", "1.jpg", "2.jpg"], leaf
     assert not os.path.exists(os.path.join(r.output_dir, "02", "depth")) and len(r.images) == 3
+
+
+# demo/taekwondo_demo.py:39-72: three edit sessions (origin / shift / scale), each = retime two performers by key frames,
+# a 101-pose smooth path, render_path with auto_save, save_video.  Executed VERBATIM from the reference's demo script when
+# a reference checkout (or the archive of oracle/stash_reference.py) is available, restated otherwise.
+DEMO_SESSIONS = '''
+key_frames_layer_1 = [21,49,74,87]
+key_frames_layer_2 = [13,42,80,90]
+key_frames = [20,50,74,85]
+density_threshold = 0
+inverse_y_axis = False
+for kw, name in (({}, 'origin'), ({'shift': [[0,0,0],[0,2,0],[0,-2,0]]}, 'shift'), ({'scale': [1,0.75,1.5]}, 'scale')):
+    neural_renderer = LayeredNeuralRenderer(cfg, **kw)
+    neural_renderer.set_save_dir(name)
+    neural_renderer.retime_by_key_frames(1, key_frames_layer_1, key_frames)
+    neural_renderer.retime_by_key_frames(2, key_frames_layer_2, key_frames)
+    neural_renderer.set_fps(25)
+    neural_renderer.set_smooth_path_poses(101, around=False)
+    neural_renderer.render_path(inverse_y_axis,density_threshold,auto_save=True)
+    neural_renderer.save_video()
+'''
+
+
+@pytest.mark.gpu
+def test_taekwondo_demo_call_sequence(tmp_path):
+    import sys
+    import render
+    sys.path.insert(0, C.ROOT)
+    from oracle import stash_reference
+    spec = dict(SP, frame_num=101, frame_offset=0, size_test=(48, 27), original=(96, 54))
+    scene, out = str(tmp_path / "scene"), str(tmp_path / "outputs")
+    os.makedirs(out)
+    C.write_synthetic_dataset(scene, spec=spec)
+    torch.save({"model": synthetic_state_dict(2, True, seed=9)}, os.path.join(out, "layered_rfnr_checkpoint_1.pt"))
+    cfg = make_render_cfg(out, scene, 2, spec["frame_num"], spec["size_test"], n1=12, n2=20, frame_offset=0,
+                          scale=spec["scale"], fixed_near=0.5, fixed_far=20.0)
+    ref = stash_reference.reference_root()
+    block, verbatim = DEMO_SESSIONS, False
+    if ref is not None:
+        lines = open(os.path.join(ref, "demo", "taekwondo_demo.py")).read().split("\n")
+        block, verbatim = "\n".join(lines[38:72]), True                  # demo/taekwondo_demo.py:39-72
+        assert "LayeredNeuralRenderer(cfg, scale=[1,0.75,1.5])" in block and "cfg.merge_from_file" not in block
+    scope = {"cfg": cfg, "LayeredNeuralRenderer": render.LayeredNeuralRenderer}
+    exec(block, scope)
+    r = scope["neural_renderer"]                                         # the last session ('scale')
+    assert r.model.scale == [1, 0.75, 1.5] and len(r.poses) == 101 and len(r.images) == 101 and r.save_count == 1
+    root = os.path.join(out, "rendered")
+    assert sorted(os.listdir(root)) == ["origin", "scale", "shift"], (verbatim, os.listdir(root))
+    for name in ("origin", "shift", "scale"):
+        base = os.path.join(root, name, "video_0")
+        assert sorted(os.listdir(base)) == ["0", "1", "2", "mixed"]
+        assert len(os.listdir(os.path.join(base, "mixed", "color"))) == 101 and len(os.listdir(os.path.join(base, "2", "depth"))) == 101
+    # the retimed timelines reached the renderer: layer 1 shows frame 21 where the new timeline says 20, ... (:46-47)
+    pairs = dict((int(a), float(b)) for a, b in r.layer_frame_pairs[20])
+    assert set(pairs) == {0, 1, 2}
+    # frame 50 of the scale session again through render_pose: same pixels as the saved take (same seed)
+    r.model.seed = r.model.seed - (101 - 50)
+    color, depth, _, _ = r.render_pose(r.poses[50], r.Ks[50], r.layer_frame_pairs[50], 0, 0)
+    assert torch.equal(color.cpu(), r.images[50])

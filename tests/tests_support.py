@@ -20,8 +20,9 @@ from stnerf_b200.config import make_cfg  # noqa: E402,F401
 
 
 def build_case_model(name, precision="exact", chunk_rays=0, sd=None):
+    """`name`: key of cases.CASES / cases.SCALE_CASES, or a case dict."""
     import modeling
-    case = C.CASES[name]
+    case = name if isinstance(name, dict) else (C.CASES[name] if name in C.CASES else C.SCALE_CASES[name])
     sd = sd if sd is not None else C.state_dict_for(case)
     if sd is None:
         return None
