@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- rays/sec of the layered ray-march hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision exact|mixed|fp32|fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision mixed|exact|fp32|fast]
+                    [--workload taekwondo2|walking4|walking6_4k] [--no-extra] [--no-cpu-baseline]
 
 Workload (BASELINE.json configs[1]): taekwondo 2-layer scene, 1080p, 16 views, 64 coarse + 128 fine samples.
-A *step* renders one 1080p view (2 073 600 rays; view = step mod 16) through the whole hot path: bbox-clipped
-sampling -> MotionNet/SpaceNet MLPs -> resampling -> fine MLPs -> per-layer + merged compositing of every
-image plane.  Scene geometry and cameras are synthetic (the dataset is not shipped); weights are
-the shipped taekwondo checkpoint when its copy is present under oracle/_ref/ckpt, else seeded random weights of
-the same architecture (the cost of the path does not depend on weight values).
+A *step* renders one 1080p view (2 073 600 rays; view = step mod 16) through the whole hot path: ray generation ->
+bbox-clipped sampling -> MotionNet/SpaceNet MLPs -> compositing + resampling -> fine MLPs -> per-layer + merged compositing
+of every image (coarse AND fine, i.e. everything `LayeredRFRender.forward` returns).  Scene geometry and cameras are
+synthetic (the dataset is not shipped); weights are the shipped taekwondo checkpoint when its copy is present
+under oracle/_ref/ckpt, else seeded random weights of the same architecture (the cost of the path does not depend on weight
+values).
 
-value  = device-resident throughput: rays already in HBM, CUDA events around the K steps, max over ranks.
-e2e    = same metric through the host-buffer C-ABI call (stnerf_render_host): pinned host rays -> H2D ->
-         render -> D2H of every image plane, inside the timed region.
-N > 1  : each view's rows are interleaved over the ranks, one all-gather of the fine image planes per view
-         (strong scaling: total work per step is fixed).
---impl reference : the CPU oracle port of the reference algorithm (torch fp32, all host threads) timed on a
-         bounded sample of the same workload; rank 0 only.
+value  = device-resident throughput: cameras/rays already on the device, CUDA events around the K steps, max over ranks.
+         N ranks: each view's rows are interleaved over the ranks, every rank's compositing kernel writes its pixels straight
+         into its slot of a persistent all-gather buffer and ONE in-place all-gather per view assembles the fine images on
+         every rank (strong scaling: total work per step is fixed).
+e2e    = same metric through the host-buffer C-ABI call (stnerf_render_host): pinned host rays -> H2D (chunk-pipelined) ->
+         render -> D2H of every image plane (chunk-pipelined), inside the timed region, same K steps.
+--impl reference : the UNMODIFIED reference (`LayeredRFRender.forward`, run out of process from the archive packed by
+         oracle/stash_reference.py) on the host cores, on a bounded sample of the same workload per step; rank 0 only.
+         Falls back to the oracle port (kind "port") only if no reference archive / checkout is available.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,48 +39,44 @@ for p in (ROOT, os.path.join(ROOT, "st-nerf_b200"), os.path.join(ROOT, "tests"),
     if p not in sys.path:
         sys.path.insert(0, p)
 
-H, W, VIEWS, N1, N2, LAYERS = 1080, 1920, 16, 64, 128, 2
-FRAME_IDS = [0.0, 10.0, 11.0]
-FLOP_SPACE_BKGD, FLOP_SPACE_PERF, FLOP_MOTION = 924672.0, 930048.0, 153344.0   # SURVEY 8(d), 2*MAC per point
-CKPT, SPACE_TIME, THR, NEAR = "taekwondo", True, (0.0, 0.0), 0.0                # demo/taekwondo_demo.py:44
-WORKLOAD_NAME = "taekwondo 2-layer 1080p, 16 views, 64+128 samples (BASELINE configs[1])"
+FLOP_SPACE_NOTIME, FLOP_SPACE_TIME, FLOP_MOTION = 924672.0, 930048.0, 153344.0   # SURVEY 8(d), 2*MAC per point
 
-# The headline line is always configs[1] (default).  The other BASELINE configs can be timed for the record with --workload.
+# BASELINE.json configs.  The headline line is always configs[1]; the others are timed briefly as `extra_workloads`.
 WORKLOADS = {
-    "taekwondo2": None,
+    "taekwondo2": dict(H=1080, W=1920, views=16, n1=64, n2=128, layers=2, ckpt="taekwondo", space_time=True, thr=(0.0, 0.0), near=0.0,
+                       frame_ids=[0.0, 10.0, 11.0], fixture="scale_tkd2_16k",                       # demo/taekwondo_demo.py:44
+                       name="taekwondo 2-layer 1080p, 16 views, 64+128 samples (BASELINE configs[1])"),
     # configs[2]: walking nets replicated round-robin to 4 performers, demo/walking_demo.py:43-50 thresholds
-    "walking4": dict(H=1080, W=1920, VIEWS=16, N1=64, N2=128, LAYERS=4, CKPT="walking", SPACE_TIME=False, THR=(20.0, 0.8),
-                     NEAR=4.0, FLOP_SPACE_PERF=924672.0,
-                     WORKLOAD_NAME="walking 4-layer 1080p, 16 views, 64+128 samples (BASELINE configs[2])"),
+    "walking4": dict(H=1080, W=1920, views=16, n1=64, n2=128, layers=4, ckpt="walking", space_time=False, thr=(20.0, 0.8), near=4.0,
+                     frame_ids=[0.0, 30.0, 31.0, 32.0, 33.0], fixture="scale_walk4_16k",
+                     name="walking 4-layer 1080p, 16 views, 64+128 samples (BASELINE configs[2])"),
     # configs[4]: 6 performers, 4K, 32 views, 64+192
-    "walking6_4k": dict(H=2160, W=3840, VIEWS=32, N1=64, N2=192, LAYERS=6, CKPT="walking", SPACE_TIME=False,
-                        THR=(20.0, 0.8), NEAR=4.0, FLOP_SPACE_PERF=924672.0,
-                        WORKLOAD_NAME="walking 6-layer 4K, 32 views, 64+192 samples (BASELINE configs[4])"),
+    "walking6_4k": dict(H=2160, W=3840, views=32, n1=64, n2=192, layers=6, ckpt="walking", space_time=False, thr=(20.0, 0.8), near=4.0,
+                        frame_ids=[0.0, 30.0, 31.0, 32.0, 33.0, 34.0, 35.0], fixture="scale_walk6_4k",
+                        name="walking 6-layer 4K, 32 views, 64+192 samples (BASELINE configs[4])"),
 }
+PRECISION_TERMS = {"exact": 3.0, "mixed": 3.0 - 2.0 * (256 * 128) / 462336.0, "fast": 1.0, "fp32": 1.0}
+DTYPES = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate",
+          "mixed": "f32 via fp16x3 split products on everything the density depends on, single f16 pass on the colour-only layer "
+                   "rgb_net.1 (tcgen05), f32 accumulate"}
 
 
-def select_workload(name):
-    w = WORKLOADS[name]
-    if w:
-        globals().update(w)
-        globals()["FRAME_IDS"] = [0.0] + [30.0 + i for i in range(w["LAYERS"])]
-
-
-def load_weights():
+def load_weights(wl):
     import torch
     from stnerf_b200 import checkpoint_io
-    p = checkpoint_io.find_checkpoint(CKPT)
+    p = checkpoint_io.find_checkpoint(wl["ckpt"])
     if p is not None:
-        sd = checkpoint_io.replicate_layers(torch.load(p, map_location="cpu")["model"], LAYERS)
-        return sd, "%s checkpoint (oracle/_ref/ckpt)%s" % (CKPT, ", nets replicated round-robin to %d performers" % LAYERS if LAYERS > 2 else "")
+        sd = checkpoint_io.replicate_layers(torch.load(p, map_location="cpu")["model"], wl["layers"])
+        return sd, "%s checkpoint (oracle/_ref/ckpt)%s" % (
+            wl["ckpt"], ", nets replicated round-robin to %d performers" % wl["layers"] if wl["layers"] > 2 else "")
     from stnerf_b200 import synthetic
-    return synthetic.synthetic_state_dict(LAYERS, SPACE_TIME, seed=7), "seeded random weights (checkpoint copy absent)"
+    return synthetic.synthetic_state_dict(wl["layers"], wl["space_time"], seed=7), "seeded random weights (checkpoint copy absent)"
 
 
-def scene_setup():
+def scene_setup(wl):
     from stnerf_b200 import synthetic              # synthetic scene description (inputs only)
-    bkgd, frames = synthetic.synthetic_boxes(LAYERS)
-    cams = [synthetic.synthetic_camera(v, VIEWS, H, W) for v in range(VIEWS)]
+    bkgd, frames = synthetic.synthetic_boxes(wl["layers"])
+    cams = [synthetic.synthetic_camera(v, wl["views"], wl["H"], wl["W"]) for v in range(wl["views"])]
     return bkgd, frames, cams
 
 
@@ -109,129 +110,146 @@ class ClockSampler:
             self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_median": statistics.median(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_rate(steps: int, warmup: int, sample_rays: int):
-    """The reference algorithm on the host cores: oracle port (kind 'port'), bounded sample per step."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference itself (kind "reference"), out of process; the oracle port only as a fallback
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sample(wl, cams, step, per_band):
+    """Rays of one step's bounded sample: 4 row bands of the step's view (representative layer hit fractions)."""
     import torch
-    from oracle import stnerf_oracle as O          # the CPU leg is the one place bench.py executes the oracle
-    sd, data = load_weights()
-    nets = O.split_state_dict(sd, LAYERS)
-    bkgd, frames, cams = scene_setup()
-    sc = O.resolve_scene(frames, bkgd, FRAME_IDS, None, None)
-    sc.update(scale=None, shift=None, shown=[True] * (LAYERS + 1), near=NEAR, alpha=1.0, boarder=1e10)
-    fid = torch.tensor(FRAME_IDS)[None]
-    times = []
-    gen = torch.Generator().manual_seed(1234)
+    from oracle import stnerf_oracle as O          # ray generation for the CPU arm only (test infrastructure)
+    H, W = wl["H"], wl["W"]
+    K, T = cams[step % wl["views"]]
+    full = O.generate_rays(K, T, H, W)
+    idx = torch.cat([torch.arange(per_band) + (H * (2 * q + 1) // 8) * W + (W - per_band) // 2 for q in range(4)])
+    fid = torch.tensor(wl["frame_ids"])[None]
+    return torch.cat([full[idx], fid.expand(idx.numel(), -1)], 1).contiguous()
 
-    def probe(nthreads):
-        """rays/s of a 256-ray sample with `nthreads` torch threads (picks the fastest host configuration)."""
-        torch.set_num_threads(nthreads)
-        K, T = cams[0]
-        full = O.generate_rays(K, T, H, W)
-        idx = torch.arange(256) + (H // 2) * W + (W - 256) // 2
-        rays = torch.cat([full[idx], fid.expand(256, -1)], 1)
-        jit, u = torch.rand((LAYERS + 1, 256, N1), generator=gen), torch.rand((LAYERS + 1, 256, N2), generator=gen)
-        best = 0.0
-        for _ in range(2):
+
+def cpu_reference_rate(wl, steps, warmup, rays_per_worker):
+    """rays/s of the reference algorithm on the host cores.  Returns (rate, ms_per_step, sample_rays, data, cores, kind, sample)."""
+    import torch
+    from oracle import stash_reference
+    import cases as C                                  # job plumbing of oracle/run_reference.py (tests/golden/cases.py)
+    sd, data = load_weights(wl)
+    bkgd, frames, cams = scene_setup(wl)
+    ncpu = os.cpu_count() or 1
+    l = wl["layers"] + 1
+    gen = torch.Generator().manual_seed(1234)
+    have_ref = stash_reference.reference_root() is not None
+    # the reference's eager fp32 ops stop scaling near 16 threads (measured on this pool's 128-thread hosts): use every core as
+    # independent workers of <= 16 threads, each on its own slice of the sample (rays are independent, SURVEY C.6)
+    workers = max(1, ncpu // 16)
+    threads = ncpu
+    per_band = max(64, (rays_per_worker * workers) // 4)
+    times = []
+    if have_ref:
+        multi = []
+        for s in range(warmup + steps):
+            rays = cpu_sample(wl, cams, s, per_band)
+            multi.append(dict(rays=rays, jitter=torch.rand((l, rays.shape[0], wl["n1"]), generator=gen),
+                              u=torch.rand((l, rays.shape[0], wl["n2"]), generator=gen)))
+        job = dict(sd=sd, L=wl["layers"], space_time=wl["space_time"], n1=wl["n1"], n2=wl["n2"], bkgd=bkgd, frames=frames,
+                   thr=tuple(wl["thr"]), near=wl["near"], alpha=1.0, hidden=[], shift=None, scale=None, multi=multi)
+        res = C.run_reference_job(job, workers=workers, threads=threads)      # one interpreter start-up per worker for the whole run
+        # per step: the slowest worker's time inside LayeredRFRender.forward on its slice of the step's sample
+        times = [(res["rays_each"][s], res["seconds_each"][s]) for s in range(warmup, warmup + steps)]
+        kind = "reference"
+        how = "unmodified reference LayeredRFRender.forward (out of process), torch fp32, %d workers x %d threads = %d of %d host threads" % (
+            workers, max(1, threads // workers), workers * max(1, threads // workers), ncpu)
+    else:
+        from oracle import stnerf_oracle as O
+        nets = O.split_state_dict(sd, wl["layers"])
+        sc = O.resolve_scene(frames, bkgd, wl["frame_ids"], None, None)
+        sc.update(scale=None, shift=None, shown=[True] * l, near=wl["near"], alpha=1.0, boarder=1e10)
+        threads = min(ncpu, 16)
+        workers = 1
+        torch.set_num_threads(threads)
+        per_band = max(64, rays_per_worker // 4)
+        for s in range(warmup + steps):
+            rays = cpu_sample(wl, cams, s, per_band)
+            jit = torch.rand((l, rays.shape[0], wl["n1"]), generator=gen)
+            u = torch.rand((l, rays.shape[0], wl["n2"]), generator=gen)
             t0 = time.perf_counter()
             with torch.no_grad():
-                O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
-            best = max(best, 256 / (time.perf_counter() - t0))
-        return best
-
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
-    rates = {c: probe(c) for c in cands}
-    threads = max(rates, key=rates.get)
-    torch.set_num_threads(threads)
-    for s in range(warmup + steps):
-        K, T = cams[s % VIEWS]
-        full = O.generate_rays(K, T, H, W)
-        # rows spread over the image so the layer hit fractions are representative (BASELINE.md section 3)
-        per = max(1, sample_rays // 4)
-        idx = torch.cat([torch.arange(per) + (H * (2 * q + 1) // 8) * W + (W - per) // 2 for q in range(4)])
-        rays = torch.cat([full[idx], fid.expand(idx.numel(), -1)], 1)
-        jit = torch.rand((LAYERS + 1, rays.shape[0], N1), generator=gen)
-        u = torch.rand((LAYERS + 1, rays.shape[0], N2), generator=gen)
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            out = O.render(nets, sc, rays, N1, N2, jit, u, density_threshold=THR[0], bkgd_density_threshold=THR[1])
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append((rays.shape[0], dt))
-    n = sum(a for a, _ in times); t = sum(b for _, b in times)
-    cpu_reference_rate.last = (rays, jit, u, out)      # the parity leg of main() re-renders these rays on the GPU
-    return n / t, t / len(times) * 1e3, rays.shape[0], data, threads
+                O.render(nets, sc, rays, wl["n1"], wl["n2"], jit, u, density_threshold=wl["thr"][0], bkgd_density_threshold=wl["thr"][1])
+            if s >= warmup:
+                times.append((rays.shape[0], time.perf_counter() - t0))
+        kind = "port"
+        how = "oracle port (no reference archive found), torch fp32, %d of %d host threads" % (threads, ncpu)
+    n = sum(a for a, _ in times)
+    t = sum(b for _, b in times)
+    cores = workers * max(1, threads // workers) if have_ref else threads
+    sample = "%d steps x %d rays (4 row bands of the step's view), full %d+%d path; %s" % (len(times), times[0][0], wl["n1"], wl["n2"], how)
+    return n / t, t / len(times) * 1e3, times[0][0], data, cores, kind, sample
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="exact", choices=["exact", "mixed", "fp32", "fast"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-rays", type=int, default=2048)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="taekwondo2", choices=list(WORKLOADS))
-    args = ap.parse_args()
-    select_workload(args.workload)
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": WORKLOAD_NAME,
-              "step": "one %dx%d view = %d rays (view = step mod %d)" % (W, H, H * W, VIEWS), "layers": LAYERS + 1, "n1": N1, "n2": N2,
-              "parallelism": "rows interleaved over %d GPU(s) + 1 all-gather of fine image planes per view" % world,
-              "l2": "no explicit flush: per-chunk working set (~1.2 GB of samples/raw/σ buffers) >> 126 MB L2"}
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def parity_vs_reference_fixture(wl, model, dev):
+    """The committed fixture of the UNMODIFIED reference for this workload (tests/golden/scale_*.npz: 16 384 / 4 096 rays of a
+    full-size view, injected uniforms) against the GPU path in the bench's precision mode."""
+    import numpy as np
+    import torch
+    import cases as C
+    case = C.SCALE_CASES[wl["fixture"]]
+    gold = C.load_golden(wl["fixture"])
+    if gold is None:
+        return None
+    rays, jit, u = C.scale_inputs(case)
+    model.inject_uniforms(jit.to(dev).contiguous(), u.to(dev).contiguous())
+    with torch.no_grad():
+        out = model(rays.to(dev), None, None, density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+    got = out[0][0].float().cpu().numpy()
+    ref = gold["fine_mixed.rgb"]
+    err = np.abs(got - ref).max(1)
+    mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+    return {"rays": int(rays.shape[0]), "max_abs_rgb_err": float(err.max()), "frac_pixels_over_1e-3": float((err > 1e-3).mean()),
+            "pixels_over_1e-3": int((err > 1e-3).sum()), "median_abs_rgb_err": float(np.median(err)),
+            "psnr_db": 99.0 if mse == 0 else float(10.0 * math.log10(1.0 / mse)),
+            "against": "unmodified reference LayeredRFRender.forward on CPU (fixture tests/golden/%s.npz), identical rays / weights / "
+                       "uniforms; pixels over 1e-3 sit on the sample_pdf denom<1e-5 branch point and are attributed one by one in "
+                       "tests/test_gpu_parity_scale.py" % wl["fixture"]}
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        rate, ms, nr, data, cores = cpu_reference_rate(args.steps, args.warmup, args.cpu_sample_rays)
-        sample = "%d rays of the step's view (4 row bands), full 64+128 path, torch fp32 on %d of %d host threads (fastest of a probe)" % (nr, cores, os.cpu_count() or 1)
-        print(json.dumps({"impl": "reference", "metric": "rays/sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic scene; " + data,
-                          "config": config,
-                          "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
-        return
 
+def measure(wl, precision, steps, warmup, rank, world, local_rank, want_e2e=True, want_parity=True):
+    """One workload on this process' GPU (all ranks call it).  Returns a dict of measurements (complete on rank 0)."""
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     import stnerf_b200 as S
     from stnerf_b200.dist import ShardedViewRenderer
-    from stnerf_b200 import _lib as L
     from stnerf_b200.config import make_cfg
+    from stnerf_b200 import ops
     import modeling
 
-    sd, data = load_weights()
-    bkgd, frames, cams = scene_setup()
-    model = modeling.build_layered_model(make_cfg(LAYERS, N1, N2, SPACE_TIME, args.precision))
+    dev = torch.device("cuda", local_rank)
+    H, W, N1, N2, LAYERS, VIEWS = wl["H"], wl["W"], wl["n1"], wl["n2"], wl["layers"], wl["views"]
+    sd, data = load_weights(wl)
+    bkgd, frames, cams = scene_setup(wl)
+    model = modeling.build_layered_model(make_cfg(LAYERS, N1, N2, wl["space_time"], precision))
     model.load_state_dict(sd)
     model.set_bkgd_bbox(bkgd); model.set_bboxes(frames)
     nat = model._ensure_native(dev)
-    model.near = NEAR
-    nat.set_scene(model._resolve_scene(torch.tensor(FRAME_IDS), THR[0], THR[1]))   # the demo's thresholds
+    model.near = wl["near"]
+    model.retiming = True
+    scene = model._resolve_scene(torch.tensor(wl["frame_ids"]), wl["thr"][0], wl["thr"][1])   # the demo's thresholds
     svr = ShardedViewRenderer(nat, H, W, N1, N2, rank, world)
-    rays_dev = [svr.rays_for(K, T, FRAME_IDS) for (K, T) in cams]               # inputs resident in HBM
-    n_local = rays_dev[0].shape[0]
+    n_local = svr.rp * W
+    nat.reserve_host(n_local, 6 + LAYERS + 1)
     rays_per_step = H * W
 
     def step(i):
-        return svr.render(rays_dev[i % VIEWS], seed=i + 1)
+        v = nat.make_view(cams[i % VIEWS][0], cams[i % VIEWS][1], wl["frame_ids"], scene, i + 1)
+        return svr.render([v], time_collective=(world > 1), with_coarse=True)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -241,9 +259,12 @@ def main():
     nat.profile_begin()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    coll_ms = []
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
+        if world > 1:
+            coll_ms.append(svr._timing)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -257,106 +278,170 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lt = torch.tensor([float(launches)], device=dev); dist.all_reduce(lt); launches = int(lt.item())
     ms_total = float(t.item())
-    value = rays_per_step * args.steps / (ms_total * 1e-3)
+    res = {"value": rays_per_step * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "clocks": clk,
+           "gpu_launches": int(launches), "data": data, "prof": prof, "n_local": n_local}
+    if world > 1:
+        ms = [a.elapsed_time(b) for a, b in coll_ms]
+        res["collective"] = {"op": "ncclAllGather, in place (send buffer = the rank's slot of the receive buffer), 1 per view",
+                             "bytes_per_rank": int((LAYERS + 2) * n_local * 5 * 4), "ms_mean": sum(ms) / len(ms), "ms_max": max(ms),
+                             "timed": "CUDA events around the collective on the compute stream (includes waiting for slower ranks)"}
 
-    # ---- e2e: host buffers through the C-ABI (H2D rays + D2H every plane inside the timed region) ----------
-    e2e = None
-    # the same views as the first steps of the timed region (cost depends on how many rays hit the performers)
-    e2e_views = [(args.warmup + i) % VIEWS for i in range(max(1, args.e2e_steps))]
-    rays_host = [rays_dev[v].cpu().pin_memory() for v in e2e_views]
-    out_host = torch.empty((2, LAYERS + 2, 5 * n_local), dtype=torch.float32).pin_memory()
-    mask_host = torch.empty((LAYERS + 1, n_local), dtype=torch.uint8).pin_memory()
-    nat.render_host(rays_host[0], N1, N2, seed=99, out_host=out_host, mask_host=mask_host)   # warm staging buffers
-    torch.cuda.synchronize()
+    # ---- e2e: host buffers through the C-ABI (H2D rays + D2H every plane inside the timed region), same step count ------
+    if want_e2e:
+        n_views_host = min(VIEWS, max(1, steps), 4)
+        rays_host = []
+        for v in range(n_views_host):
+            K, T = cams[(warmup + v) % VIEWS]
+            r = ops.generate_rays(K, T, H, W, frame_ids=wl["frame_ids"], row0=rank, row_step=world, n_rows=svr.rp)
+            rays_host.append(r.cpu().pin_memory())
+            del r
+        out_host = torch.empty((2, LAYERS + 2, 5 * n_local), dtype=torch.float32).pin_memory()
+        mask_host = torch.empty((LAYERS + 1, n_local), dtype=torch.uint8).pin_memory()
+        nat.set_scene(scene)
+        nat.render_host(rays_host[0], N1, N2, seed=99, out_host=out_host, mask_host=mask_host)   # warm
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            nat.render_host(rays_host[i % n_views_host], N1, N2, seed=100 + i, out_host=out_host, mask_host=mask_host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        res["e2e"] = {"value": rays_per_step * steps / float(te.item()), "unit": "rays/s",
+                      "h2d_bytes_per_step": int(rays_host[0].numel() * 4 * world),
+                      "d2h_bytes_per_step": int((out_host.numel() * 4 + mask_host.numel()) * world),
+                      "api": "stnerf_render_host (C-ABI, pinned host buffers; rays up and image planes down chunk by chunk on copy "
+                             "streams while other chunks render), %d steps, max over ranks of the host wall clock" % steps}
+    if want_parity and rank == 0:
+        res["parity"] = parity_vs_reference_fixture(wl, model, dev)
+    del svr, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_of(wl, res, precision, steps, peaks):
+    prof, n_local = res["prof"], res["n_local"]
+    N1, N2, LAYERS = wl["n1"], wl["n2"], wl["layers"]
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    sp = prof["spacenet"]
+    # algorithmic FLOPs: 2*MAC per evaluated point (nets with a PE(time) input have the wider rgb head); the split between
+    # background and performer points comes from the per-launch point counts
+    pts = sp["points"]
+    bk_pts = float(n_local) * (N1 + N1 + N2) * steps
+    flop_perf = FLOP_SPACE_TIME if wl["space_time"] else FLOP_SPACE_NOTIME
+    flops = bk_pts * FLOP_SPACE_NOTIME + max(0.0, pts - bk_pts) * flop_perf
+    ach = flops / (sp["ms"] * 1e-3) / 1e12 if sp["ms"] > 0 else 0.0
+    terms = PRECISION_TERMS[precision]
+    traffic, traffic_note = None, None
+    try:      # DRAM bytes per point of the same kernel from the committed `ncu --set full` capture, scaled to the mean launch
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_spacenet_traffic.json")))
+        traffic = cap["dram_bytes_per_point"] * pts / max(1, sp["launches"])
+        traffic_note = ("NOT measured in this run: dram__bytes_read+write per point (%.1f B) from the committed ncu --set full capture "
+                        "profiles/r01_spacenet_traffic.json (%s) x this run's mean points per launch" % (cap["dram_bytes_per_point"], cap["kernel"]))
+    except Exception:
+        pass
+    ms_total = res["ms_per_step"] * steps
+    roof = {"kernel": "spacenet MLP (%s)" % precision, "bound": "tensor", "achieved": ach, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": ach / peak_tf, "executed": ach * terms, "frac_executed": ach * terms / peak_tf,
+            "peak_source": ("measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1400 (B200_PROFILING.md)"),
+            "traffic": traffic, "traffic_note": traffic_note, "launches": sp["launches"], "avg_launch_ms": sp["ms"] / max(1, sp["launches"]),
+            "share_of_step": sp["ms"] / ms_total,
+            "note": "achieved/frac = algorithmic FLOPs (2*MAC/point x points evaluated) / CUDA-event launch durations of this run; the split modes "
+                    "execute %.2f fp16 MMAs per product (frac is capped at 1/%.2f), executed/frac_executed = what the tensor pipe runs" % (terms, terms),
+            "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "spacenet"}}
+    # compositing + resampling kernels: algorithmic bytes (depths + raw rgb-sigma in, depths + images out) against the HBM peak,
+    # reported for completeness -- they are instruction-issue-bound (sort / search / scan per sample), see DESIGN.md
+    cp = prof["composite"]
+    hit_frac = max(0.0, pts - bk_pts) / max(1.0, bk_pts)
+    bytes_comp = float(n_local) * steps * ((1 + hit_frac) * (N1 * 24 + (N1 + N2) * 20 + (N1 + N2) * 4) + (LAYERS + 2) * 40)
+    roof["composite_hbm"] = {"achieved_GBps": bytes_comp / (cp["ms"] * 1e-3) / 1e9 if cp["ms"] > 0 else 0.0,
+                             "peak_GBps": peaks.get("hbm_gbs", 6650.0), "share_of_step": cp["ms"] / ms_total}
+    return roof
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="mixed", choices=["exact", "mixed", "fp32", "fast"])
+    ap.add_argument("--cpu-sample-rays", type=int, default=1024, help="rays per CPU worker per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--workload", default="taekwondo2", choices=list(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    H, W = wl["H"], wl["W"]
+    config = {"workload": wl["name"],
+              "step": "one %dx%d view = %d rays (view = step mod %d), coarse + fine images of every layer" % (W, H, H * W, wl["views"]),
+              "layers": wl["layers"] + 1, "n1": wl["n1"], "n2": wl["n2"],
+              "parallelism": "rows interleaved over %d GPU(s); compositing kernel writes into the rank's slot of a persistent buffer; "
+                             "1 in-place all-gather of the fine images per view" % world,
+              "l2": "no explicit flush: per-chunk working set (~1.2 GB of samples/raw rgb-sigma buffers) >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rate, ms, nr, data, cores, kind, sample = cpu_reference_rate(wl, args.steps, args.warmup, args.cpu_sample_rays)
+        print(json.dumps({"impl": "reference", "metric": "rays/sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic scene; " + data,
+                          "config": config,
+                          "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        nat.render_host(rays_host[i], N1, N2, seed=100 + i, out_host=out_host, mask_host=mask_host)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": rays_per_step * args.e2e_steps / float(te.item()), "unit": "rays/s",
-           "h2d_bytes_per_step": int(rays_host[0].numel() * 4 * world),
-           "d2h_bytes_per_step": int((out_host.numel() * 4 + mask_host.numel()) * world),
-           "api": "stnerf_render_host (C-ABI, pinned host buffers), %d steps" % args.e2e_steps}
+        dist.init_process_group("nccl", device_id=dev)
+    res = measure(wl, args.precision, args.steps, args.warmup, rank, world, local_rank)
+
+    extra = {}
+    if not args.no_extra and args.workload == "taekwondo2":
+        # the other BASELINE configs, briefly (1 warm-up + 2 / 1 timed steps): driver-visible lines, not the headline
+        for name, (k, w_) in (("walking4", (2, 1)), ("walking6_4k", (1, 1))):
+            try:
+                r = measure(WORKLOADS[name], args.precision, k, w_, rank, world, local_rank, want_e2e=False, want_parity=True)
+                extra[name] = {"workload": WORKLOADS[name]["name"], "value": r["value"], "unit": "rays/s", "ms_per_step": r["ms_per_step"],
+                               "steps": k, "warmup": w_, "n_gpus": world, "parity": r.get("parity"), "collective": r.get("collective"),
+                               "spacenet_share_of_step": r["prof"]["spacenet"]["ms"] / (r["ms_per_step"] * k)}
+            except Exception as e:                       # an extra line must never take the headline down with it
+                extra[name] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (SpaceNet MLP) from live CUDA-event timings ----------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    sp = prof["spacenet"]
-    # algorithmic FLOPs: 2*MAC per evaluated point (taekwondo performer nets have the wider rgb head);
-    # the split between background and performer points comes from the per-launch point counts
-    pts = sp["points"]
-    bk_pts = float(n_local) * (N1 + N1 + N2) * args.steps
-    flops = bk_pts * FLOP_SPACE_BKGD + max(0.0, pts - bk_pts) * FLOP_SPACE_PERF
-    ach = flops / (sp["ms"] * 1e-3) / 1e12 if sp["ms"] > 0 else 0.0
-    # executed MMA terms per algorithmic product: 3 (exact); mixed runs rgb_net.1 (256x128 of the 462 336 MAC/point) in one pass
-    terms = {"exact": 3.0, "mixed": 3.0 - 2.0 * (256 * 128) / 462336.0}.get(args.precision, 1.0)
-    traffic, traffic_note = None, None
-    try:      # DRAM bytes per point of the same kernel from the committed `ncu --set full` capture, scaled to the mean launch
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_spacenet_traffic.json")))
-        traffic = cap["dram_bytes_per_point"] * pts / max(1, sp["launches"])
-        traffic_note = "dram__bytes_read+write per point (%.1f B, ncu --set full: %s) x mean points per launch" % (
-            cap["dram_bytes_per_point"], cap["kernel"])
-    except Exception:
-        pass
-    roof = {"kernel": "spacenet MLP (%s)" % args.precision, "bound": "tensor", "achieved": ach, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": ach / peak_tf, "executed": ach * terms, "frac_executed": ach * terms / peak_tf,
-            "peak_source": ("measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1400 (B200_PROFILING.md)"),
-            "traffic": traffic, "traffic_note": traffic_note, "launches": sp["launches"], "avg_launch_ms": sp["ms"] / max(1, sp["launches"]),
-            "share_of_step": sp["ms"] / ms_total,
-            "note": "achieved/frac = algorithmic FLOPs (2*MAC/point x points evaluated); exact mode executes 3 fp16 MMAs per product "
-                    "(frac is capped at 1/3), executed/frac_executed = what the tensor pipe runs",
-            "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "spacenet"}}
-    # compositing kernel against the HBM roofline (algorithmic bytes: l*S*20 B in per ray-pass + outputs)
-    cp = prof["composite"]
-    hit_frac = max(0.0, pts - bk_pts) / max(1.0, bk_pts)
-    bytes_comp = float(n_local) * args.steps * ((1 + hit_frac) * (N1 * 24 + (N1 + N2) * 20 + (N1 + N2) * 4) + (LAYERS + 2) * 40)
-    roof["composite_hbm"] = {"achieved_GBps": bytes_comp / (cp["ms"] * 1e-3) / 1e9 if cp["ms"] > 0 else 0.0,
-                             "peak_GBps": peaks.get("hbm_gbs", 6650.0)}
+    roof = roofline_of(wl, res, args.precision, args.steps, peaks)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, _, nr, _, cores = cpu_reference_rate(3, 1, args.cpu_sample_rays)
-        cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": "3 steps x %d rays (4 row bands of the view), full 64+128 path, torch fp32, %d of %d host threads (fastest of a probe)" % (nr, cores, os.cpu_count() or 1)}
+        rate, _, nr, _, cores, kind, sample = cpu_reference_rate(wl, 2, 1, args.cpu_sample_rays)
+        cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample}
 
-    parity = None
-    if cpu is not None and getattr(cpu_reference_rate, "last", None) is not None:
-        # same rays / weights / uniforms through the GPU path vs the CPU oracle (itself pinned to the reference)
-        rays_c, jit_c, u_c, want = cpu_reference_rate.last
-        nat.set_ray_ids(0, 0, 0)
-        outp, _ = nat.render(rays_c.to(dev), N1, N2, jitter=jit_c.to(dev).contiguous(), u=u_c.to(dev).contiguous(), seed=1)
-        fm, _, _, _ = S.split_planes(outp, LAYERS + 1)
-        got = fm[0].float().cpu()
-        ref = want["fine_mixed"][0]
-        err = (got - ref).abs().max(dim=1)[0]
-        mse = float(((got - ref) ** 2).mean())
-        parity = {"rays": int(rays_c.shape[0]), "max_abs_rgb_err": float(err.max()),
-                  "frac_pixels_over_1e-3": float((err > 1e-3).float().mean()),
-                  "psnr_db": (99.0 if mse == 0 else float(10.0 * __import__("math").log10(1.0 / mse))),
-                  "against": "CPU oracle port (pinned to the reference by tests/golden), identical rays/weights/uniforms"}
-
-    dtype = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate",
-             "mixed": "f32 via fp16x3 split products on the density path, single f16 pass on the colour-only layer rgb_net.1 (tcgen05), f32 accumulate"}[args.precision]
-    print(json.dumps({"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                      "scaling": "strong", "vs_baseline": None, "dtype": dtype,
-                      "data": "synthetic scene + cameras (SURVEY 8d); " + data, "config": config, "clocks": clk,
-                      "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                      "parity": parity, "precision": args.precision}))
+    print(json.dumps({"metric": "rays/sec", "value": res["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": DTYPES[args.precision],
+                      "data": "synthetic scene + cameras (SURVEY 8d); " + res["data"], "config": config, "clocks": res["clocks"],
+                      "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"], "roofline": roof, "cpu_baseline": cpu,
+                      "parity": res.get("parity"), "collective": res.get("collective"), "precision": args.precision,
+                      "extra_workloads": extra or None}))
     if world > 1:
         dist.destroy_process_group()
 

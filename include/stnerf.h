@@ -125,10 +125,42 @@ int stnerf_render(stnerf_handle h, const float* rays, int64_t n_rays, int ray_st
  * row_stride = n_ranks * W so that every pixel gets the same draws as in an unsharded render of the same seed.         */
 int stnerf_set_ray_ids(stnerf_handle h, int64_t base, int32_t width, int64_t row_stride);
 
-/* Same call with HOST buffers (pinned or pageable): H2D of rays, render, D2H of out/ray_mask on `stream`,
- * returns after the stream has drained.  This is the e2e path bench.py times.                             */
+/* Same call with HOST buffers (pinned for overlap; pageable works, serialised by the driver): the rays go up chunk by chunk
+ * on a copy stream while earlier chunks render, every finished chunk's slices of out / ray_mask come down on a second copy
+ * stream while later chunks render; returns after everything has drained.  Replaces the `.cuda()` ... `.cpu()` bracket of
+ * render_pose (render/layered_neural_renderer.py:372-392, 451-454).  This is the e2e path bench.py times.
+ * Device staging is sized by stnerf_reserve_host; a call larger than anything reserved (re)allocates it first.            */
 int stnerf_render_host(stnerf_handle h, const float* rays_host, int64_t n_rays, int ray_stride, int n1, int n2,
                        int only_coarse, uint64_t seed, float* out_host, uint8_t* ray_mask_host, void* stream);
+/* Pre-size the device staging of the host-buffer entry points (rays, image planes, masks, per-view image buffers, copy
+ * streams and events) for calls of up to `max_rays` rays, so that those calls allocate nothing.                            */
+int stnerf_reserve_host(stnerf_handle h, int64_t max_rays, int ray_stride);
+
+/* ---- the renderer-facing fast path: LayeredNeuralRenderer.render_pose / render_path ------------------------------------ */
+/* (render/layered_neural_renderer.py:364-392, 401-488; data/datasets/ray_dataset.py:260-283 for the rays of a pose.)
+ * One entry of a batch of poses: camera, the per-layer frame ids of the pose (`layer_frame_pair`, ray_dataset.py:276-279),
+ * the scene constants of THIS frame (boxes lerped to these frame ids, per-frame shift/scale/alpha edits
+ * render/layered_neural_renderer.py:435-440, thresholds) and the seed of its Philox stream.  All host memory.           */
+typedef struct {
+  float Kinv[9];                                 /* inverse intrinsics, row-major                                              */
+  float T[16];                                   /* camera-to-world, row-major                                                  */
+  float frame_ids[STNERF_MAX_LAYERS];            /* column 6+i of every ray of this view                                        */
+  stnerf_scene scene;
+  uint64_t seed;
+} stnerf_view;
+/* Renders rows row0, row0+row_step, ... (n_rows of them) of an HxW image for each of n_views poses in ONE call: rays are
+ * generated on the device (never cross PCIe), and only what render_pose returns is produced -- the FINE images, mixed + one per
+ * layer, pixel-interleaved: images[v*view_stride + (img*n_rows*W + pixel)*5 + {0,1,2: rgb, 3: depth, 4: acc}].  With
+ * coarse_images == NULL the coarse pass only resamples (no coarse images, no merged coarse composite); with a buffer of the same
+ * shape it also produces the coarse images, i.e. everything LayeredRFRender.forward returns (modeling/layered_rfrender.py:725-734).  The last requested row may lie one row_step past H-1 (equal
+ * shard sizes when H is not a multiple of row_step): it is rendered as an extrapolated pixel row the caller discards.  Enqueue only; `images` is a DEVICE buffer -- e.g. one
+ * rank's slice of an all-gather buffer when the rows of a view are interleaved over GPUs (row0 = rank, row_step = ranks).    */
+int stnerf_render_views(stnerf_handle h, const stnerf_view* views_host, int n_views, int H, int W, int row0, int row_step,
+                        int n_rows, int n1, int n2, float* images, float* coarse_images, int64_t view_stride, void* stream);
+/* Full HxW frames to a HOST buffer ([n_views][l+1][H*W][5], pinned for overlap): the device->host copy of view v runs on a
+ * copy stream while view v+1 renders (two device image buffers); returns after the last copy has landed.                   */
+int stnerf_render_views_host(stnerf_handle h, const stnerf_view* views_host, int n_views, int H, int W, int n1, int n2,
+                             float* images_host, void* stream);
 
 /* ---- ray generation: utils/render_helpers.py:96-123 == utils/ray_sampling.py:22-72 --------------------- */
 /* Kinv_host = inverse(K) (3x3 row-major), T_host = camera-to-world (4x4 row-major).  Writes rows

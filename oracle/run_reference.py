@@ -19,6 +19,8 @@ the reference through this command-line program.
                   exactly the sample positions another implementation chose)
     perturb_seed  int: multiply every coarse weight handed to `sample_pdf` by (1 + s*2^-23), s = -1/0/+1 drawn per element
                   from this seed (a +-1-ulp perturbation of the resampling input)
+    multi         list of {rays, jitter, u}: time SEVERAL inputs in one process (bench.py's steps: one interpreter start-up for
+                  the whole run); the result then carries "seconds_each" (per input) and the outputs of the last input only
 `result.pt`: {"flat": cases.flatten_outputs schema (numpy), "seconds": wall time of the forward calls, "threads": T, ...}.
 
 Rays are processed in chunks of 3584 like `layered_batchify_ray` (utils/batchify_rays.py:57); `--workers W` splits the rays
@@ -40,6 +42,10 @@ CHUNK = 512 * 7
 
 def _slice_job(job, a, b):
     out = dict(job)
+    if "multi" in job:                     # slice every input the same way (relative bounds: a, b are fractions here)
+        out["multi"] = [_slice_job(dict(rays=m["rays"], jitter=m["jitter"], u=m.get("u")),
+                                   int(a * m["rays"].shape[0]), int(b * m["rays"].shape[0])) for m in job["multi"]]
+        return out
     out["rays"] = job["rays"][a:b].clone()
     out["jitter"] = job["jitter"][:, a:b].clone()
     for k in ("u", "z_override"):
@@ -61,12 +67,13 @@ def _cat_results(parts):
 
 def run_workers(job, workers, threads):
     import torch
-    n = job["rays"].shape[0]
+    multi = "multi" in job
+    n = 0 if multi else job["rays"].shape[0]
     per = (n + workers - 1) // workers
     tmp = tempfile.mkdtemp(prefix="stnerf_refjob_")
     procs = []
     for w in range(workers):
-        a, b = w * per, min(n, (w + 1) * per)
+        a, b = (w / workers, (w + 1) / workers) if multi else (w * per, min(n, (w + 1) * per))
         if a >= b:
             break
         jin, jout = os.path.join(tmp, "in%d.pt" % w), os.path.join(tmp, "out%d.pt" % w)
@@ -80,6 +87,10 @@ def run_workers(job, workers, threads):
         parts.append(torch.load(jout, weights_only=False))
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
+    if multi:
+        k = len(parts[0]["seconds_each"])
+        return {"seconds_each": [max(p["seconds_each"][i] for p in parts) for i in range(k)],
+                "rays_each": [sum(p["rays_each"][i] for p in parts) for i in range(k)], "threads": sum(p["threads"] for p in parts)}
     return _cat_results(parts)
 
 
@@ -116,6 +127,19 @@ def run_single(job, threads):
     model.alpha = job.get("alpha", 1.0)
     for i in job.get("hidden", []):
         model.hide_layer(i)
+    if "multi" in job:                      # several inputs, timed one after the other in this one process
+        secs, counts = [], []
+        for m in job["multi"]:
+            sub = dict(job); sub.pop("multi"); sub.update(rays=m["rays"], jitter=m["jitter"], u=m.get("u"))
+            r = _run_inputs(sub, model, R, LR, torch, np)
+            secs.append(r["seconds"]); counts.append(int(m["rays"].shape[0]))
+        return {"seconds_each": secs, "rays_each": counts, "threads": threads}
+    res = _run_inputs(job, model, R, LR, torch, np)
+    res["threads"] = threads
+    return res
+
+
+def _run_inputs(job, model, R, LR, torch, np):
     rays, jit, u = job["rays"], job["jitter"], job.get("u")
     only_coarse = bool(job.get("only_coarse", False))
     record = bool(job.get("record", False))
@@ -175,7 +199,7 @@ def run_single(job, threads):
     coarse_layer = [cat_trip(lambda o, i=i: o[3][i]) for i in range(l)]
     ray_mask = [torch.cat([o[4][i].reshape(-1) for o in outs], 0) for i in range(l)]
     res = {"flat": flatten_outputs(fine_mixed, coarse_mixed, fine_layer, coarse_layer, ray_mask), "seconds": secs,
-           "threads": threads, "rays": n, "reference_root": R.REFERENCE_ROOT}
+           "rays": n, "reference_root": R.REFERENCE_ROOT}
     if record:
         res["record"] = {k: np.stack([torch.cat(v[i], 0).numpy() for i in range(l)], 0) for k, v in rec.items()}
     return res

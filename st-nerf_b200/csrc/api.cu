@@ -56,6 +56,11 @@ struct stnerf_ctx {
   float *h_rays = nullptr, *h_out = nullptr;
   uint8_t* h_mask = nullptr;
   size_t h_rays_bytes = 0, h_out_bytes = 0, h_mask_bytes = 0;
+  // staging for stnerf_render_views(_host): rays of one view, two image buffers (double-buffered device->host copies)
+  float *v_rays = nullptr, *v_img[2] = {nullptr, nullptr};
+  size_t v_rays_bytes = 0, v_img_bytes[2] = {0, 0};
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;      // host<->device copies that overlap the kernels of other chunks
+  std::vector<cudaEvent_t> ev_pool;                         // timing-disabled events, reused call after call
   int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
   RayIdMap idmap{0, 0, 0};     // stnerf_set_ray_ids
   // profiling (stnerf_profile_begin / _end): CUDA-event pairs around every launch, on the launching stream
@@ -184,6 +189,10 @@ void stnerf_destroy(stnerf_handle c) {
     for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->space[f][i].blob); tc_free(c->space[f][i].tc); }
   for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->motion[i].blob); tc_free(c->motion[i].tc); }
   cudaFree(c->h_rays); cudaFree(c->h_out); cudaFree(c->h_mask); cudaFree(c->any_frac);
+  cudaFree(c->v_rays); cudaFree(c->v_img[0]); cudaFree(c->v_img[1]);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->prof_counts) cudaFreeHost(c->prof_counts);
   delete c;
 }
@@ -499,11 +508,24 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
   return STNERF_OK;
 }
 
-extern "C" {
+// Where the images of a call go.  `coarse` / `fine`: [l+1 images][5*n_total floats] each (image 0 mixed, 1+i layer i), or null =
+// that pass writes no images (the coarse pass then only resamples: its merged composite is skipped altogether).
+struct OutSpec {
+  float* coarse;
+  float* fine;
+  int pixels;            // 0: image = rgb (N,3) | depth (N) | acc (N) planes;  1: image = (N,5) pixel-interleaved
+};
 
-int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_stride, int n1, int n2, int only_coarse,
-                  const float* jitter, const float* u, uint64_t seed, float* out, uint8_t* ray_mask, void* stream) {
-  if (!c || !rays || !out || n_rays < 0) return STNERF_EINVAL;
+// Called after the last kernel of a chunk has been enqueued (pipelined host copies hang their events here).
+struct ChunkHook {
+  int (*fn)(void* user, long long c0, long long n, cudaStream_t st);
+  void* user;
+};
+
+static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int ray_stride, int n1, int n2, int only_coarse,
+                       const float* jitter, const float* u, uint64_t seed, OutSpec out, uint8_t* ray_mask, cudaStream_t st,
+                       const ChunkHook* before_chunk = nullptr, const ChunkHook* after_chunk = nullptr) {
+  if (!c || !rays || n_rays < 0) return STNERF_EINVAL;
   if (!c->have_scene) return STNERF_EINVAL;
   {                                         // the context's weights and workspace live on the device it was created on
     int cur = -1;
@@ -514,14 +536,15 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
   if (n1 < 3 || n1 > STNERF_MAX_N1) return STNERF_EINVAL;
   if (only_coarse) n2 = 0;
   if (n2 < 0 || n1 + n2 > STNERF_MAX_S) return STNERF_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (n2 == 0 && !out.coarse) return STNERF_EINVAL;
+  if (n2 > 0 && !out.fine) return STNERF_EINVAL;
   int rc = ensure_ws(c, n1, n1 + n2);
   if (rc) return rc;
   const int l = c->l, S2 = n1 + n2;
   const long long R = c->chunk_rays, N = n_rays;
-  const long long plane = 5 * N;
   for (long long c0 = 0; c0 < N; c0 += R) {
     const long long n = std::min(R, N - c0);
+    if (before_chunk) { rc = before_chunk->fn(before_chunk->user, c0, n, st); if (rc) return rc; }
     c->last_chunk_rays = n; c->last_n1 = n1; c->last_s2 = n2 > 0 ? S2 : 0;
     const float* rch = rays + c0 * ray_stride;
     STNERF_CUDA(cudaMemsetAsync(c->counts, 0, STNERF_MAX_LAYERS * 4, st));
@@ -550,7 +573,7 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
     a.mask = mask; a.mask_layer_stride = mask_ls;
     a.u = u ? u + c0 * n2 : nullptr; a.u_layer_stride = N * n2;
     a.t_fine = c->t_fine; a.tf_layer_stride = R * c->cap_s2;
-    a.out = out; a.n_total = N; a.ray_base = c0; a.n = n;
+    a.out = out.coarse; a.pixel_layout = out.pixels; a.n_total = N; a.ray_base = c0; a.n = n;
     a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed; a.idmap = c->idmap;
     {
       ProfScope ps(c, 3, (double)n, -1, 1, st);
@@ -563,14 +586,24 @@ int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_st
       a.t = c->t_fine; a.t_layer_stride = R * c->cap_s2;
       a.raw = c->raw_fine; a.raw_layer_stride = R * c->cap_s2 * 4;
       a.u = nullptr; a.t_fine = nullptr;
-      a.out = out + (size_t)(l + 1) * plane;
+      a.out = out.fine;
       a.S = S2; a.n2 = 0; a.fine = 1;
       ProfScope ps(c, 3, (double)n, -1, 1, st);
       rc = launch_composite_pass(a, c->dscene, l, st);
       if (rc) return rc;
     }
+    if (after_chunk) { rc = after_chunk->fn(after_chunk->user, c0, n, st); if (rc) return rc; }
   }
   return STNERF_OK;
+}
+
+extern "C" {
+
+int stnerf_render(stnerf_handle c, const float* rays, int64_t n_rays, int ray_stride, int n1, int n2, int only_coarse,
+                  const float* jitter, const float* u, uint64_t seed, float* out, uint8_t* ray_mask, void* stream) {
+  if (!c || !out) return STNERF_EINVAL;
+  OutSpec o{out, out + (size_t)(c->l + 1) * 5 * (size_t)n_rays, 0};
+  return render_core(c, rays, n_rays, ray_stride, n1, n2, only_coarse, jitter, u, seed, o, ray_mask, (cudaStream_t)stream);
 }
 
 static int grow(void** p, size_t* have, size_t want) {
@@ -582,23 +615,181 @@ static int grow(void** p, size_t* have, size_t want) {
   return STNERF_OK;
 }
 
+}  // extern "C"
+
+// ---- host-buffer plumbing: copy streams, an event pool, per-chunk hooks ------------------------------------------------------
+static int ensure_copy_streams(stnerf_ctx* c) {
+  if (!c->copy_in) STNERF_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  if (!c->copy_out) STNERF_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  return STNERF_OK;
+}
+static int ensure_events(stnerf_ctx* c, size_t n) {
+  while (c->ev_pool.size() < n) {
+    cudaEvent_t e;
+    STNERF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  return STNERF_OK;
+}
+
+namespace {
+// stnerf_render_host: rays arrive chunk by chunk on `copy_in` while earlier chunks render; the image slices of a finished chunk
+// leave on `copy_out` while later chunks render.
+struct HostPipe {
+  stnerf_ctx* c;
+  long long N;
+  int only_coarse;
+  float* out_host;
+  uint8_t* mask_host;
+  size_t ev_in0, ev_out0;      // first event index of the per-chunk "rays landed" / "chunk rendered" events
+};
+int host_before_chunk(void* user, long long c0, long long, cudaStream_t st) {
+  HostPipe* p = static_cast<HostPipe*>(user);
+  const size_t k = (size_t)(c0 / p->c->chunk_rays);
+  STNERF_CUDA(cudaStreamWaitEvent(st, p->c->ev_pool[p->ev_in0 + k], 0));
+  return STNERF_OK;
+}
+int host_after_chunk(void* user, long long c0, long long n, cudaStream_t st) {
+  HostPipe* p = static_cast<HostPipe*>(user);
+  stnerf_ctx* c = p->c;
+  const size_t k = (size_t)(c0 / c->chunk_rays);
+  cudaEvent_t done = c->ev_pool[p->ev_out0 + k];
+  STNERF_CUDA(cudaEventRecord(done, st));
+  STNERF_CUDA(cudaStreamWaitEvent(c->copy_out, done, 0));
+  const size_t N = (size_t)p->N, plane = 5 * N;
+  const int n_img = (p->only_coarse ? 1 : 2) * (c->l + 1);
+  for (int im = 0; im < n_img; ++im) {      // plane = rgb (N,3) | depth (N) | acc (N): three contiguous slices per chunk
+    const float* src = c->h_out + (size_t)im * plane;
+    float* dst = p->out_host + (size_t)im * plane;
+    STNERF_CUDA(cudaMemcpyAsync(dst + 3 * (size_t)c0, src + 3 * (size_t)c0, (size_t)n * 12, cudaMemcpyDeviceToHost, c->copy_out));
+    STNERF_CUDA(cudaMemcpyAsync(dst + 3 * N + c0, src + 3 * N + c0, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    STNERF_CUDA(cudaMemcpyAsync(dst + 4 * N + c0, src + 4 * N + c0, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_out));
+  }
+  if (p->mask_host)
+    for (int i = 0; i < c->l; ++i)
+      STNERF_CUDA(cudaMemcpyAsync(p->mask_host + (size_t)i * N + c0, c->h_mask + (size_t)i * N + c0, (size_t)n,
+                                  cudaMemcpyDeviceToHost, c->copy_out));
+  return STNERF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int stnerf_reserve_host(stnerf_handle c, int64_t max_rays, int ray_stride) {
+  if (!c || max_rays <= 0 || ray_stride < 6) return STNERF_EINVAL;
+  const size_t n = (size_t)max_rays;
+  int rc = grow((void**)&c->h_rays, &c->h_rays_bytes, n * ray_stride * 4);
+  rc |= grow((void**)&c->h_out, &c->h_out_bytes, (size_t)2 * (c->l + 1) * 5 * n * 4);
+  rc |= grow((void**)&c->h_mask, &c->h_mask_bytes, (size_t)c->l * n);
+  rc |= grow((void**)&c->v_rays, &c->v_rays_bytes, n * (6 + STNERF_MAX_LAYERS) * 4);
+  for (int b = 0; b < 2; ++b) rc |= grow((void**)&c->v_img[b], &c->v_img_bytes[b], (size_t)(c->l + 1) * 5 * n * 4);
+  if (rc) return STNERF_ENOMEM;
+  rc = ensure_copy_streams(c);
+  if (rc) return rc;
+  return ensure_events(c, 2 * (size_t)((max_rays + c->chunk_rays - 1) / c->chunk_rays) + 8);
+}
+
 int stnerf_render_host(stnerf_handle c, const float* rays_host, int64_t n_rays, int ray_stride, int n1, int n2,
                        int only_coarse, uint64_t seed, float* out_host, uint8_t* ray_mask_host, void* stream) {
   if (!c || !rays_host || !out_host || n_rays <= 0) return STNERF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rb = (size_t)n_rays * ray_stride * 4, ob = (size_t)2 * (c->l + 1) * 5 * n_rays * 4,
                mb = (size_t)c->l * n_rays;
+  if (only_coarse) n2 = 0;
+  // staging: sized by stnerf_reserve_host; grown here only when a call exceeds every earlier size
   int rc = grow((void**)&c->h_rays, &c->h_rays_bytes, rb);
   rc |= grow((void**)&c->h_out, &c->h_out_bytes, ob);
   rc |= grow((void**)&c->h_mask, &c->h_mask_bytes, mb);
   if (rc) return STNERF_ENOMEM;
-  STNERF_CUDA(cudaMemcpyAsync(c->h_rays, rays_host, rb, cudaMemcpyHostToDevice, st));
-  rc = stnerf_render(c, c->h_rays, n_rays, ray_stride, n1, n2, only_coarse, nullptr, nullptr, seed, c->h_out, c->h_mask, st);
+  rc = ensure_copy_streams(c);
   if (rc) return rc;
-  const size_t ob_used = only_coarse ? ob / 2 : ob;
-  STNERF_CUDA(cudaMemcpyAsync(out_host, c->h_out, ob_used, cudaMemcpyDeviceToHost, st));
-  if (ray_mask_host) STNERF_CUDA(cudaMemcpyAsync(ray_mask_host, c->h_mask, mb, cudaMemcpyDeviceToHost, st));
-  STNERF_CUDA(cudaStreamSynchronize(st));
+  const long long R = c->chunk_rays;
+  const size_t n_chunks = (size_t)((n_rays + R - 1) / R);
+  rc = ensure_events(c, 2 * n_chunks + 1);
+  if (rc) return rc;
+  // the copy-in stream starts after everything already queued on `st` (the staging buffers may still be read by it)
+  cudaEvent_t start = c->ev_pool[2 * n_chunks];
+  STNERF_CUDA(cudaEventRecord(start, st));
+  STNERF_CUDA(cudaStreamWaitEvent(c->copy_in, start, 0));
+  STNERF_CUDA(cudaStreamWaitEvent(c->copy_out, start, 0));
+  for (size_t k = 0; k < n_chunks; ++k) {
+    const long long c0 = (long long)k * R, n = std::min<long long>(R, n_rays - c0);
+    STNERF_CUDA(cudaMemcpyAsync(c->h_rays + (size_t)c0 * ray_stride, rays_host + (size_t)c0 * ray_stride, (size_t)n * ray_stride * 4,
+                                cudaMemcpyHostToDevice, c->copy_in));
+    STNERF_CUDA(cudaEventRecord(c->ev_pool[k], c->copy_in));
+  }
+  HostPipe pipe{c, n_rays, n2 == 0 ? 1 : 0, out_host, ray_mask_host, 0, n_chunks};
+  ChunkHook before{host_before_chunk, &pipe}, after{host_after_chunk, &pipe};
+  OutSpec o{c->h_out, c->h_out + (size_t)(c->l + 1) * 5 * (size_t)n_rays, 0};
+  rc = render_core(c, c->h_rays, n_rays, ray_stride, n1, n2, only_coarse, nullptr, nullptr, seed, o, c->h_mask, st, &before, &after);
+  // drain both streams even on an error so no copy is left in flight into the caller's buffers
+  cudaError_t e1 = cudaStreamSynchronize(c->copy_out), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(c->copy_in);
+  if (rc) return rc;
+  STNERF_CUDA(e1); STNERF_CUDA(e2); STNERF_CUDA(e3);
+  return STNERF_OK;
+}
+
+// One view of stnerf_render_views: rays of the requested rows generated on the device, scene constants of THIS view, fine images
+// written pixel-interleaved to `images` ([l+1][n_rows*W][5]).  Enqueue only.
+static int render_one_view(stnerf_ctx* c, const stnerf_view* v, int H, int W, int row0, int row_step, int n_rows, int n1, int n2,
+                           float* images, float* coarse_images, cudaStream_t st) {
+  const long long n = (long long)n_rows * W;
+  const int stride = 6 + c->l;
+  int rc = stnerf_set_scene(c, &v->scene);
+  if (rc) return rc;
+  if (c->scene.shared_frame_id) return STNERF_EINVAL;          // views carry one frame id per layer (retiming rays)
+  rc = launch_raygen(v->Kinv, v->T, H, W, row0, row_step, n_rows, v->frame_ids, c->l, c->v_rays, stride, st);
+  if (rc) return rc;
+  const RayIdMap keep = c->idmap;
+  c->idmap = RayIdMap{(long long)row0 * W, (long long)row_step * W, W};       // every pixel keeps the draws of an unsharded render
+  OutSpec o{coarse_images, images, 1};
+  rc = render_core(c, c->v_rays, n, stride, n1, n2, 0, nullptr, nullptr, v->seed, o, nullptr, st);
+  c->idmap = keep;
+  return rc;
+}
+
+int stnerf_render_views(stnerf_handle c, const stnerf_view* views_host, int n_views, int H, int W, int row0, int row_step,
+                        int n_rows, int n1, int n2, float* images, float* coarse_images, int64_t view_stride, void* stream) {
+  if (!c || !views_host || !images || n_views < 1 || H < 1 || W < 1 || row0 < 0 || row_step < 1 || n_rows < 1 || n2 < 1)
+    return STNERF_EINVAL;
+  if (row0 >= H || row0 + (long long)(n_rows - 1) * row_step >= H + row_step) return STNERF_EINVAL;   // at most one padding row
+  const size_t n = (size_t)n_rows * W;
+  if (view_stride < (int64_t)((size_t)(c->l + 1) * 5 * n)) return STNERF_EINVAL;
+  if (grow((void**)&c->v_rays, &c->v_rays_bytes, n * (6 + c->l) * 4)) return STNERF_ENOMEM;
+  for (int v = 0; v < n_views; ++v) {
+    const int rc = render_one_view(c, views_host + v, H, W, row0, row_step, n_rows, n1, n2, images + (size_t)v * view_stride,
+                                   coarse_images ? coarse_images + (size_t)v * view_stride : nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return STNERF_OK;
+}
+
+int stnerf_render_views_host(stnerf_handle c, const stnerf_view* views_host, int n_views, int H, int W, int n1, int n2,
+                             float* images_host, void* stream) {
+  if (!c || !views_host || !images_host || n_views < 1 || H < 1 || W < 1 || n2 < 1) return STNERF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)H * W, img_floats = (size_t)(c->l + 1) * 5 * n;
+  int rc = grow((void**)&c->v_rays, &c->v_rays_bytes, n * (6 + c->l) * 4);
+  for (int b = 0; b < 2; ++b) rc |= grow((void**)&c->v_img[b], &c->v_img_bytes[b], img_floats * 4);
+  if (rc) return STNERF_ENOMEM;
+  rc = ensure_copy_streams(c);
+  if (rc) return rc;
+  rc = ensure_events(c, 4);
+  if (rc) return rc;
+  // events 0/1: "view rendered into buffer b";  2/3: "buffer b copied out"
+  for (int v = 0; v < n_views && rc == STNERF_OK; ++v) {
+    const int b = v & 1;
+    if (v >= 2) STNERF_CUDA(cudaStreamWaitEvent(st, c->ev_pool[2 + b], 0));       // buffer b is free again
+    rc = render_one_view(c, views_host + v, H, W, 0, 1, H, n1, n2, c->v_img[b], nullptr, st);
+    if (rc) break;
+    STNERF_CUDA(cudaEventRecord(c->ev_pool[b], st));
+    STNERF_CUDA(cudaStreamWaitEvent(c->copy_out, c->ev_pool[b], 0));
+    STNERF_CUDA(cudaMemcpyAsync(images_host + (size_t)v * img_floats, c->v_img[b], img_floats * 4, cudaMemcpyDeviceToHost, c->copy_out));
+    STNERF_CUDA(cudaEventRecord(c->ev_pool[2 + b], c->copy_out));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(c->copy_out), e2 = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  STNERF_CUDA(e1); STNERF_CUDA(e2);
   return STNERF_OK;
 }
 

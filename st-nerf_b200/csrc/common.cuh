@@ -166,7 +166,8 @@ struct CompositeArgs {
   long long u_layer_stride;
   float* t_fine;           // out (coarse pass with n2 > 0): [layer][ray][n1+n2]
   long long tf_layer_stride;
-  float* out;              // planes of this pass: [img][5*n_total]
+  float* out;              // images of this pass: [img][5*n_total], or null (coarse pass: resampling only, no images)
+  int pixel_layout;        // 0: plane = rgb (N,3) | depth (N) | acc (N);  1: plane = (N,5) pixel-interleaved
   long long n_total;       // rays in the whole call (plane geometry)
   long long ray_base;      // first ray of this chunk within the call
   long long n;             // rays in this chunk

@@ -120,6 +120,15 @@ __device__ __forceinline__ void composite_run(int count, At at, Rgb rgb_at, cons
   out[3] = warp_sum(cd); out[4] = warp_sum(ca);
 }
 
+// One image pixel (rgb, depth, acc) of ray `rg`: plane layout rgb (N,3) | depth (N) | acc (N), or 5 interleaved floats.
+__device__ __forceinline__ void write_pixel(float* img, long long rg, long long n_total, bool pixels, const float o5[5], int lane) {
+  if (img == nullptr || lane >= 5) return;
+  const float v = lane == 0 ? o5[0] : lane == 1 ? o5[1] : lane == 2 ? o5[2] : lane == 3 ? o5[3] : o5[4];
+  if (pixels) img[rg * 5 + lane] = v;
+  else if (lane < 3) img[rg * 3 + lane] = v;
+  else img[(long long)lane * n_total + rg] = v;
+}
+
 // utils/sample_pdf.py:18-63 for one ray: t[n1] (any order), w[n1] full weights, n2 uniforms -> z written to
 // zbuf[0..n2).  cdf is an (n1-1)-float scratch.
 template <typename U>
@@ -207,6 +216,7 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
   const float near_p = scene.near_plane, boarder = scene.boarder;
   const bool thr_on = scene.apply_thr != 0;
   const long long plane = 5 * a.n_total;
+  const bool pixels = a.pixel_layout != 0;
   unsigned shown_mask = 1u;
   for (int i = 1; i < n_layers; ++i) shown_mask |= (scene.shown[i] != 0 ? 1u : 0u) << i;
 
@@ -216,12 +226,11 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
     unsigned slot_layers = 0;                     // 4 bits per gathered list: which layer it is
     bool all_asc = true;                          // every gathered list is non-decreasing (always true for fine passes)
     for (int i = 0; i < n_layers; ++i) {
-      float* oimg = a.out + (size_t)(1 + i) * plane;
+      float* oimg = a.out ? a.out + (size_t)(1 + i) * plane : nullptr;
       const bool hit = (i == 0) || (a.mask[i * a.mask_layer_stride + r] != 0);
       if (!hit) {                                 // all samples at t=-1000 with sigma 0: inert
-        if (lane < 3) oimg[rg * 3 + lane] = 0.0f;
-        if (lane == 3) oimg[3 * a.n_total + rg] = 0.0f;
-        if (lane == 4) oimg[4 * a.n_total + rg] = 0.0f;
+        const float z5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        write_pixel(oimg, rg, a.n_total, pixels, z5, lane);
         continue;
       }
       const bool shown = (shown_mask >> i) & 1u;
@@ -266,9 +275,7 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
                       return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
                     },
                     s_t, s_sig, boarder, 0.f, false, want_w ? s_w : nullptr, lane, o5);
-      if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
-      if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
-      if (lane == 4) oimg[4 * a.n_total + rg] = o5[4];
+      write_pixel(oimg, rg, a.n_total, pixels, o5, lane);
       __syncwarp();
       if (want_w) {
         // hierarchical resampling of this layer (layered_rfrender.py:459-463)
@@ -310,7 +317,7 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
       n_m += S;
     }
     // ---- merged composite over every hit layer's samples, ordered by (t, cat index)  (:425-448 / :587-606)
-    {
+    if (a.out != nullptr) {
       const int n_lists = n_m / S;
       if (all_asc) {
         // every list is sorted: the stable (t, cat index) order is a rank computation -- position of sample (h,k) =
@@ -353,10 +360,7 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
                       return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
                     },
                     s_t, s_sig, boarder, near_p, fine, nullptr, lane, o5);
-      float* oimg = a.out;
-      if (lane < 3) oimg[rg * 3 + lane] = (lane == 0) ? o5[0] : (lane == 1) ? o5[1] : o5[2];
-      if (lane == 3) oimg[3 * a.n_total + rg] = o5[3];
-      if (lane == 4) oimg[4 * a.n_total + rg] = o5[4];
+      write_pixel(a.out, rg, a.n_total, pixels, o5, lane);
       __syncwarp();
     }
   }

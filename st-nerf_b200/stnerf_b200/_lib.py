@@ -34,6 +34,12 @@ class Scene(C.Structure):
                 ("apply_thresholds", C.c_int32), ("shared_frame_id", C.c_int32)]
 
 
+class View(C.Structure):
+    """stnerf_view: one pose of a stnerf_render_views batch."""
+    _fields_ = [("Kinv", C.c_float * 9), ("T", C.c_float * 16), ("frame_ids", C.c_float * MAX_LAYERS), ("scene", Scene),
+                ("seed", C.c_uint64)]
+
+
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 4), ("points", C.c_double * 4), ("launches", C.c_uint64 * 4)]
 
@@ -54,6 +60,10 @@ _SIGNATURES = {
     "stnerf_set_scene": (C.c_int, [_P, C.POINTER(Scene)]),
     "stnerf_render": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "stnerf_render_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
+    "stnerf_reserve_host": (C.c_int, [_P, C.c_int64, C.c_int]),
+    "stnerf_render_views": (C.c_int, [_P, C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       _P, _P, C.c_int64, _P]),
+    "stnerf_render_views_host": (C.c_int, [_P, C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "stnerf_raygen": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "stnerf_intersect_sample": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "stnerf_composite": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_float, _P, _P, _P, _P, _P]),

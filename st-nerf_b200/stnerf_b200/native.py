@@ -132,6 +132,62 @@ class NativeRenderer:
                                            L.ptr(mask_host), L.stream_ptr()), "stnerf_render_host")
         return out_host, mask_host
 
+    def reserve_host(self, max_rays: int, ray_stride: int):
+        """Pre-size the device staging of render_host / render_views_host (stnerf_reserve_host): those calls then allocate nothing."""
+        L.check(L.lib().stnerf_reserve_host(self._h, int(max_rays), int(ray_stride)), "stnerf_reserve_host")
+
+    # ---- renderer-facing fast path: a batch of poses per native call (stnerf_render_views) -----------------------------------
+    @staticmethod
+    def make_view(K, T, frame_ids, scene: "L.Scene", seed: int) -> "L.View":
+        """K (3,3), T (4,4) host tensors / arrays; frame_ids: one per layer; scene: the prologue's constants for this frame."""
+        v = L.View()
+        Kinv = torch.inverse(torch.as_tensor(K, dtype=torch.float32, device="cpu")).contiguous().reshape(-1)
+        Th = torch.as_tensor(T, dtype=torch.float32, device="cpu").contiguous().reshape(-1)
+        for i in range(9):
+            v.Kinv[i] = float(Kinv[i])
+        for i in range(16):
+            v.T[i] = float(Th[i])
+        for i, f in enumerate(frame_ids):
+            v.frame_ids[i] = float(f)
+        C.memmove(C.byref(v.scene), C.byref(scene), C.sizeof(L.Scene))
+        v.seed = int(seed) & (2 ** 64 - 1)
+        return v
+
+    def render_views(self, views: Sequence["L.View"], H: int, W: int, n1: int, n2: int, row0: int = 0, row_step: int = 1,
+                     n_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                     coarse_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Fine images of every view, (n_views, l+1, n_rows*W, 5) = rgb, depth, acc per pixel, on the device.  Rays are generated
+        on the device; `out` may be any contiguous CUDA fp32 tensor with that many elements per view (e.g. a slice of an
+        all-gather buffer).  `coarse_out` (same shape): also produce the coarse images (everything forward() returns).
+        Enqueue only."""
+        n_rows = (H - row0 + row_step - 1) // row_step if n_rows is None else int(n_rows)
+        nv = len(views)
+        arr = (L.View * nv)(*views)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        per = (self.l + 1) * n_rows * W * 5
+        if out is None:
+            out = torch.empty((nv, self.l + 1, n_rows * W, 5), dtype=torch.float32, device=dev)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == nv * per
+        if coarse_out is not None:
+            assert coarse_out.is_cuda and coarse_out.dtype == torch.float32 and coarse_out.is_contiguous() and coarse_out.numel() == nv * per
+        L.check(L.lib().stnerf_render_views(self._h, arr, nv, int(H), int(W), int(row0), int(row_step), n_rows, int(n1), int(n2),
+                                            L.ptr(out), L.ptr(coarse_out), per, L.stream_ptr()), "stnerf_render_views")
+        return out
+
+    def render_views_host(self, views: Sequence["L.View"], H: int, W: int, n1: int, n2: int,
+                          out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Full frames to pinned host memory, (n_views, l+1, H*W, 5); the copy of view v overlaps the rendering of view v+1.
+        Returns after the last copy has landed."""
+        nv = len(views)
+        arr = (L.View * nv)(*views)
+        if out_host is None:
+            out_host = torch.empty((nv, self.l + 1, H * W, 5), dtype=torch.float32).pin_memory()
+        assert (not out_host.is_cuda) and out_host.dtype == torch.float32 and out_host.is_contiguous()
+        assert out_host.numel() == nv * (self.l + 1) * H * W * 5
+        L.check(L.lib().stnerf_render_views_host(self._h, arr, nv, int(H), int(W), int(n1), int(n2), L.ptr(out_host),
+                                                 L.stream_ptr()), "stnerf_render_views_host")
+        return out_host
+
     # ---- per-stage entry points that need the networks ------------------------------------------------------
     def spacenet(self, layer: int, fine: bool, pos, dirs, times=None):
         P = pos.shape[0]

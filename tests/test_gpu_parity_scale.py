@@ -102,6 +102,11 @@ def attribute_outliers(case, model, rays, jit, u, idx, flat_full):
     n = sel.numel()
     tc = [nat.read_depths(False, i, n, n1).cpu().numpy() for i in range(l)]
     tf = [nat.read_depths(True, i, n, n1 + n2).cpu().numpy() for i in range(l)]
+    dump = os.path.join(C.ROOT, "gpurun_out")
+    if os.path.isdir(dump):              # raw material for offline analysis of the attribution (scratch, not asserted on)
+        np.savez_compressed(os.path.join(dump, "attrib_%s_%s.npz" % (case["name"], model.precision)), sel=sel.numpy(), n_out=idx.size,
+                            **{"tc%d" % i: tc[i] for i in range(l)}, **{"tf%d" % i: tf[i] for i in range(l)},
+                            **{"sub." + k: v for k, v in sub.items()})
     for key in ("fine_mixed.rgb",):      # rays are independent: the sub-render reproduces the pixels of the full render
         assert np.abs(sub[key] - flat_full[key][sel.numpy()]).max() <= 2e-6
     job = C.reference_job(case, r_s, j_s, u_s, record=True)
@@ -139,7 +144,7 @@ def attribute_outliers(case, model, rays, jit, u, idx, flat_full):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(C.SCALE_CASES))
 def test_parity_at_scale_vs_reference(name):
-    case = C.SCALE_CASES[name]
+    case = dict(C.SCALE_CASES[name], name=name)
     gold = C.load_golden(name)
     if gold is None or C.state_dict_for(case) is None:
         pytest.skip("fixture or checkpoint copy absent")

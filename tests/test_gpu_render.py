@@ -143,28 +143,44 @@ def test_large_call_properties():
         assert m.any() and not m.all()
 
 
+def _views_for(model, nat, K, T, frame_ids, seed, thr=(0.0, 0.0)):
+    scene = model._resolve_scene(torch.tensor(frame_ids, dtype=torch.float32), thr[0], thr[1])
+    return [nat.make_view(K, T, frame_ids, scene, seed)]
+
+
 def test_row_sharded_render_equals_unsharded():
     """Multi-GPU layout on one device: rendering the rows of rank 0/2 and rank 1/2 separately (in-kernel Philox keyed by
-    the global pixel id) and interleaving them equals the unsharded image bit for bit."""
+    the global pixel id), each straight into its slot of the gather buffer, equals the unsharded image bit for bit
+    (SURVEY section 4, item 3).  H is odd: the last rank's padding row is rendered and discarded."""
     from oracle import stnerf_oracle as O
-    from stnerf_b200.dist import ShardedViewRenderer, assemble_image
+    from stnerf_b200.dist import ShardedViewRenderer, rows_view
     name = "syn_L2_64_128"
     case = C.CASES[name]
     model = build_case_model(name, "exact")
     dev = torch.device("cuda", 0)
     nat = model._ensure_native(dev)
-    nat.set_scene(model._resolve_scene(torch.tensor(case["frame_ids"]), 0.0, 0.0))
-    H, W = 54, 96
+    H, W = 55, 96
     K, T = O.synthetic_camera(2, 16, H, W)
+    views = _views_for(model, nat, K, T, case["frame_ids"], seed=5)
     full = ShardedViewRenderer(nat, H, W, 64, 128, 0, 1)
-    img = full.render(full.rays_for(K, T, case["frame_ids"]), seed=5).clone()
-    parts = []
+    img = full.assembled(full.render(views)).clone()                    # (1, l+1, H, W, 5)
+    assert tuple(img.shape) == (1, 3, H, W, 5)
+    buf = None
     for r in range(2):
         sh = ShardedViewRenderer(nat, H, W, 64, 128, r, 2)
-        parts.append(sh.render_local(sh.rays_for(K, T, case["frame_ids"]), seed=5).clone())   # no process group here
-    both = assemble_image(torch.stack(parts, 0), H, W, 2)
+        if buf is not None:
+            sh._gather[1] = buf                                           # both "ranks" share one gather buffer: no process group here
+        buf = sh.render_local(views)
+    both = sh.assembled(rows_view(buf, W))
     assert torch.equal(both, img)
-    assert torch.isfinite(img).all() and img[0, ..., 4].max() <= 1 + 1e-5
+    assert torch.isfinite(img).all() and img[0, 0, ..., 4].max() <= 1 + 1e-5
+    # the plane-layout entry point on explicit rays of the same view and seed: same pixels, other layout
+    from stnerf_b200 import ops, split_planes
+    nat.set_scene(model._resolve_scene(torch.tensor(case["frame_ids"], dtype=torch.float32), 0.0, 0.0))
+    rays = ops.generate_rays(K, T, H, W, frame_ids=case["frame_ids"])
+    out, _ = nat.render(rays, 64, 128, seed=5)
+    fm, _, fl, _ = split_planes(out, 3)
+    assert torch.equal(fm[0].reshape(H, W, 3), img[0, 0, ..., :3]) and torch.equal(fl[2][1].reshape(H, W), img[0, 3, ..., 3])
 
 
 def test_pose_renderer_matches_forward_on_device_rays():
@@ -195,7 +211,64 @@ def test_pose_renderer_matches_forward_on_device_rays():
     for i in range(3):
         assert torch.equal(color_layer[i], stage2_layer[i][0].reshape(H, W, 3))
         assert torch.equal(depth_layer[i], stage2_layer[i][1].reshape(H, W, 1) / 20.0)
-    # path form: asynchronous D2H, CPU tensors
-    frames = list(pr.render_path([T, T], [K, K], [pairs, pairs], density_threshold=0.3, bkgd_density_threshold=0.05))
-    assert len(frames) == 2 and not frames[0][0].is_cuda and frames[1][0].shape == (H, W, 3)
-    assert torch.isfinite(frames[1][0]).all()
+    # path form: several poses per native call (batch 2 of 3 frames), device->host copies inside the call, CPU tensors
+    pr.batch = 2
+    seed1 = model.seed
+    frames = list(pr.render_path([T, T, T], [K, K, K], [pairs, pairs, pairs], density_threshold=0.3, bkgd_density_threshold=0.05))
+    assert len(frames) == 3 and not frames[0][0].is_cuda and frames[1][0].shape == (H, W, 3)
+    model.seed = seed1 + 1                               # frame 1 of the path again, alone: same seed -> same pixels
+    c1, d1, _, dl1 = pr.render_pose(T, K, pairs, density_threshold=0.3, bkgd_density_threshold=0.05)
+    assert torch.equal(frames[1][0], c1.cpu()) and torch.equal(frames[1][3][2], dl1[2].cpu())
+    assert float((frames[1][1] - d1.cpu()).abs().max()) <= 1e-7
+
+
+def test_render_pose_against_the_oracle():
+    """`PoseRenderer.render_pose` against the CPU oracle (pinned to the reference) fed the very uniforms the kernels draw
+    (host restatement of the Philox stream): colours within the 1e-3 gate, and the post-processing of
+    render/layered_neural_renderer.py:380-390 -- negative mixed depths clamped to 0, everything divided by `far`, the
+    per-layer zeroing that tests the ALREADY clamped mixed depth and therefore never fires."""
+    from oracle import stnerf_oracle as O
+    from stnerf_b200 import PoseRenderer
+    from tests_support import philox_draws
+    name = "tkd_64_128"
+    case = C.CASES[name]
+    sd = C.state_dict_for(case)
+    if sd is None:
+        pytest.skip("checkpoint copy absent")
+    H, W, far = 40, 64, 20.0
+    K, T = O.synthetic_camera(5, 16, H, W)
+    pairs = [(0, 0), (1, 10.5), (2, 11.25)]                 # fractional frame ids: bbox lerp + MotionNet lerp
+    ids = [0.0, 10.5, 11.25]
+    thr = (0.5, 0.05)
+    for prec, tol in (("fp32", 2e-4), ("exact", 1e-3)):
+        model = build_case_model(name, prec)
+        model.near = -1.0                                   # no near cut ...
+        pr = PoseRenderer(model, H, W, far=far)
+        seed = model.seed + 1
+        color, depth, color_layer, depth_layer = pr.render_pose(T, K, pairs, density_threshold=thr[0], bkgd_density_threshold=thr[1])
+        # the oracle on the same pixels and draws
+        rays = torch.cat([O.generate_rays(K, T, H, W), torch.tensor(ids)[None].expand(H * W, -1)], 1)
+        jit, u = philox_draws(seed, 3, H * W, case["n1"], case["n2"])
+        bkgd, frames = C.boxes_for(case)
+        sc = O.resolve_scene(frames, bkgd, ids, None, None)
+        sc.update(scale=None, shift=None, shown=[True] * 3, near=-1.0, alpha=1.0, boarder=1e10)
+        with torch.no_grad():
+            want = O.render(O.split_state_dict(sd, 2), sc, rays, case["n1"], case["n2"], jit, u, density_threshold=thr[0],
+                            bkgd_density_threshold=thr[1])
+        w_color = want["fine_mixed"][0].reshape(H, W, 3)
+        w_depth = want["fine_mixed"][1].reshape(H, W, 1).clone()
+        w_depth[w_depth < 0] = 0                                                     # :382
+        w_depth = w_depth / far                                                      # :383
+        assert float((color.cpu() - w_color).abs().max()) < tol, prec
+        assert float((depth.cpu() - w_depth).abs().max()) < (2e-2 + 2e-3 * 20) / far
+        assert float(depth.min()) >= 0.0
+        for i in range(3):
+            wl = want["fine_layer"][i]
+            assert float((color_layer[i].cpu() - wl[0].reshape(H, W, 3)).abs().max()) < tol, (prec, i)
+            d1 = wl[1].reshape(H, W, 1).clone()
+            d1[w_depth < 0] = 0                                                      # :387 -- never true after :382
+            assert float((depth_layer[i].cpu() - d1 / far).abs().max()) < (2e-2 + 2e-3 * 20) / far
+            # rays that miss layer i: exactly zero colour and depth in its image (SURVEY C.6)
+            miss = ~want["ray_mask"][i].reshape(H, W)
+            assert (color_layer[i].cpu()[miss] == 0).all() and (depth_layer[i].cpu()[miss] == 0).all()
+        del model

@@ -72,3 +72,35 @@ def compare(flat, gold, keys=None):
         else:
             rep[k] = float(np.abs(flat[k].astype(np.float64) - gold[k]).max())
     return rep
+
+
+# ---- host restatement of the in-kernel Philox4x32-10 stream (csrc/common.cuh: philox_uniform) ---------------------------------
+# Lets a test hand the CPU oracle exactly the uniforms the kernels draw when none are injected: jitter of layer i = stream i,
+# resampling uniforms of layer i = stream 64+i, counter = (ray id lo, ray id hi, idx >> 2, stream), key = seed, lane = idx & 3.
+def philox_uniforms(seed: int, stream: int, ray_ids, count: int) -> np.ndarray:
+    """(len(ray_ids), count) float32 uniforms in [0,1) with 24 random bits."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    ray_ids = np.asarray(ray_ids, dtype=np.uint64)[:, None]
+    blk = (np.arange(count, dtype=np.uint64) >> np.uint64(2))[None, :]
+    mask = np.uint64(0xFFFFFFFF)
+    c0 = np.broadcast_to(ray_ids & mask, (ray_ids.shape[0], count)).copy()
+    c1 = np.broadcast_to(ray_ids >> np.uint64(32), c0.shape).copy()
+    c2 = np.broadcast_to(blk, c0.shape).copy()
+    c3 = np.full(c0.shape, stream, dtype=np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    lane = (np.arange(count) & 3)[None, :]
+    v = np.where(lane == 0, c0, np.where(lane == 1, c1, np.where(lane == 2, c2, c3)))
+    return ((v >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
+def philox_draws(seed: int, l: int, n_rays: int, n1: int, n2: int, ray_ids=None):
+    """jitter (l, n_rays, n1), u (l, n_rays, n2) as torch tensors: the draws of a render call with this seed."""
+    ids = np.arange(n_rays, dtype=np.uint64) if ray_ids is None else ray_ids
+    jit = np.stack([philox_uniforms(seed, i, ids, n1) for i in range(l)], 0)
+    u = np.stack([philox_uniforms(seed, 64 + i, ids, n2) for i in range(l)], 0)
+    return torch.from_numpy(jit), torch.from_numpy(u)
