@@ -204,6 +204,11 @@ int stnerf_weights_import(stnerf_handle h, const void* host_buf, size_t bytes);
 /* Tensor-core plumbing self-test: one 128x128x64 fp16 UMMA through the library's descriptors, swizzled layout, bulk
  * copy and TMEM load; writes max |D - host reference| (expected < 1e-3).                                     */
 int stnerf_selftest_umma(float* max_err_host);
+/* Accumulation probe: the same 128x256x64 product of all-POSITIVE fp16 operands accumulated `reps` times into one TMEM
+ * accumulator (4*reps MMAs of K=16).  Reports max |D - fp64 sum| and the mean SIGNED relative error: how the tensor core
+ * rounds when it adds into an fp32 accumulator (a negative mean growing with reps = round-toward-zero accumulation), which
+ * bounds how close the fp16x3 split can get to the reference's fp32 GEMMs.                          */
+int stnerf_selftest_umma_accum(int reps, float* max_err_host, float* mean_signed_rel_err_host);
 /* The same through the CTA-pair protocol (`tcgen05.mma.cta_group::2`, M = 256 over the two CTAs of a cluster: remote mbarrier
  * arrives, multicast commit, paired TMEM allocation): one 256x256x64 product; expected < 1e-3.                 */
 int stnerf_selftest_umma_pair(float* max_err_host);

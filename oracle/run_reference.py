@@ -17,8 +17,12 @@ the reference through this command-line program.
                   centres the sample is interpolated between (:61), cdf_hi (l,N,n2), t_coarse (l,N,n1)
     z_override    (l,N,n2): `sample_pdf` returns these depths instead of its own (the reference's fine pass then runs on
                   exactly the sample positions another implementation chose)
-    perturb_seed  int: multiply every coarse weight handed to `sample_pdf` by (1 + s*2^-23), s = -1/0/+1 drawn per element
-                  from this seed (a +-1-ulp perturbation of the resampling input)
+    perturb_seed  int: multiply every coarse weight handed to `sample_pdf` by (1 + s*perturb_rel), s = -1/0/+1 drawn per
+                  element from this seed; perturb_rel defaults to 2^-23 (a +-1-ulp perturbation of the resampling input)
+    sigma_scale   float: multiply the density every SpaceNet returns (modeling/spacenet.py:139) by this factor -- a coherent
+                  relative perturbation of all densities, coarse and fine
+    variants      list of dicts, each overriding some of {perturb_seed, perturb_rel, thr, z_override, record}: run the SAME rays
+                  once per variant in this one process; the result is {"variants": [result dict per variant]}
     multi         list of {rays, jitter, u}: time SEVERAL inputs in one process (bench.py's steps: one interpreter start-up for
                   the whole run); the result then carries "seconds_each" (per input) and the outputs of the last input only
 `result.pt`: {"flat": cases.flatten_outputs schema (numpy), "seconds": wall time of the forward calls, "threads": T, ...}.
@@ -134,6 +138,12 @@ def run_single(job, threads):
             r = _run_inputs(sub, model, R, LR, torch, np)
             secs.append(r["seconds"]); counts.append(int(m["rays"].shape[0]))
         return {"seconds_each": secs, "rays_each": counts, "threads": threads}
+    if "variants" in job:                   # the same rays under several perturbations / overrides, one process
+        outs = []
+        for var in job["variants"]:
+            sub = dict(job); sub.pop("variants"); sub.update(var)
+            outs.append(_run_inputs(sub, model, R, LR, torch, np))
+        return {"variants": outs, "threads": threads}
     res = _run_inputs(job, model, R, LR, torch, np)
     res["threads"] = threads
     return res
@@ -156,7 +166,7 @@ def _run_inputs(job, model, R, LR, torch, np):
         if pseed is not None:
             g = torch.Generator().manual_seed(int(pseed) * 1000003 + (job.get("ray_base", 0) + state["c0"]) * 31 + i)
             s = torch.randint(-1, 2, weights.shape, generator=g).to(weights.dtype)
-            weights = weights * (1.0 + s * 2.0 ** -23)
+            weights = weights * (1.0 + s * float(job.get("perturb_rel", 2.0 ** -23)))
         z = real_sample_pdf(z_vals, weights, N_samples, det=det, pytest=pytest)
         if record:
             # what utils/sample_pdf.py:20-61 computed on the way (same ops, same order; torch.rand pops the SAME u again
@@ -179,6 +189,13 @@ def _run_inputs(job, model, R, LR, torch, np):
         return z
 
     LR.sample_pdf = wrapped
+    sig_scale = job.get("sigma_scale")
+    hooks = []
+    if sig_scale is not None:
+        def scale_density(_m, _inp, out):
+            return (out[0], out[1] * float(sig_scale))
+        nets = [model.bkgd_spacenet, model.bkgd_spacenet_fine] + list(model.spacenets) + list(model.spacenets_fine)
+        hooks = [n_.register_forward_hook(scale_density) for n_ in nets]
     outs, secs = [], 0.0
     try:
         for c0 in range(0, n, CHUNK):
@@ -191,6 +208,8 @@ def _run_inputs(job, model, R, LR, torch, np):
             outs.append(out)
     finally:
         LR.sample_pdf = real_sample_pdf
+        for h in hooks:
+            h.remove()
     # concatenate the 5-tuples of the chunks (what layered_batchify_ray does, utils/batchify_rays.py:84-140)
     def cat_trip(get):
         return tuple(torch.cat([get(o)[k] for o in outs], 0) for k in range(3))

@@ -6,6 +6,7 @@
 //          -> same nets (fine weights) on n1+n2 depths -> per-layer + merged composite.
 #include <algorithm>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -61,6 +62,7 @@ struct stnerf_ctx {
   size_t v_rays_bytes = 0, v_img_bytes[2] = {0, 0};
   cudaStream_t copy_in = nullptr, copy_out = nullptr;      // host<->device copies that overlap the kernels of other chunks
   std::vector<cudaEvent_t> ev_pool;                         // timing-disabled events, reused call after call
+  bool no_fuse = false;        // STNERF_NO_FUSE=1 in the environment at create: keep the coarse compositing in its own kernel (A/B)
   int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
   RayIdMap idmap{0, 0, 0};     // stnerf_set_ray_ids
   // profiling (stnerf_profile_begin / _end): CUDA-event pairs around every launch, on the launching stream
@@ -176,6 +178,7 @@ int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   c->num_sms = prop.multiProcessorCount;
   c->precision = d->precision;
   c->chunk_rays = d->chunk_rays > 0 ? d->chunk_rays : 65536;
+  if (const char* e = getenv("STNERF_NO_FUSE")) c->no_fuse = (e[0] == '1');
   if (cudaMalloc((void**)&c->any_frac, 4) != cudaSuccess) { delete c; return STNERF_ENOMEM; }
   *out = c;
   return STNERF_OK;
@@ -448,7 +451,7 @@ static void fill_edit(PointSrc& s, const stnerf_scene& sc, int layer, bool fine)
 }
 
 static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, float* raw, float* rgb, float* sigma,
-                        cudaStream_t st, int count_slot = -1) {
+                        cudaStream_t st, int count_slot = -1, const FuseCoarse* fuse = nullptr) {
   if (!net.loaded) return STNERF_ENOWEIGHTS;
   ProfScope ps(c, 0, (double)src.n_slots * src.S, count_slot, src.S, st);
   if (c->precision == STNERF_PREC_FP32_SIMT)
@@ -460,7 +463,7 @@ static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, fl
     STNERF_CUDA(cudaFreeAsync(cb, st));
     return rc;
   }
-  return tc_launch_spacenet(src, net.tc, net.w, c->precision, c->cbuf, raw, rgb, sigma, c->num_sms, st);
+  return tc_launch_spacenet(src, net.tc, net.w, c->precision, c->cbuf, raw, rgb, sigma, c->num_sms, st, fuse);
 }
 static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, const int* lerp_flag, int lerp_force,
                          float* xyz_out, float* flow_out, cudaStream_t st, int count_slot = -1) {
@@ -471,8 +474,11 @@ static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, 
   return tc_launch_motionnet(src, net.tc, net.w, c->precision, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st);
 }
 
+// `fuse` (coarse pass only): template of the per-layer fusion request (everything but the layer-specific fields), or null.
+// `want_raw`: the (rgb, sigma) samples must reach HBM (a later kernel composites them); false only with `fuse`.
 static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_stride, bool fine, int S, cudaStream_t st,
-                    int chunk_slot) {
+                    int chunk_slot, const FuseCoarse* fuse = nullptr, bool want_raw = true, float* coarse_imgs = nullptr,
+                    long long plane = 0) {
   const long long R = c->chunk_rays;
   const float* tbuf = fine ? c->t_fine : c->t_coarse;
   float* rawbuf = fine ? c->raw_fine : c->raw_coarse;
@@ -487,11 +493,20 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     s.S = S; s.layer = c->scene.shared_frame_id ? 0 : i;      // frame-id column offset of this layer
     s.pos_stride = 3; s.time_stride = 1;
     fill_edit(s, c->scene, i, fine);
-    float* raw = rawbuf + (size_t)i * tl * 4;
+    float* raw = want_raw ? rawbuf + (size_t)i * tl * 4 : nullptr;
+    FuseCoarse f;
+    memset(&f, 0, sizeof(f));
+    if (fuse) {
+      f = *fuse;
+      f.on = 1; f.layer = i; f.is_bkgd = (i == 0);
+      f.t_fine = c->t_fine + (size_t)i * R * c->cap_s2;
+      f.u = fuse->u ? fuse->u + (size_t)i * fuse->n_total * fuse->n2 : nullptr;     // [layer][ray of the call][n2], chunk offset applied by the caller
+      f.img = coarse_imgs ? coarse_imgs + (size_t)(1 + i) * plane : nullptr;
+    }
     int rc;
     if (i == 0) {
       s.hit = nullptr; s.count = nullptr; s.n_slots = n;
-      rc = run_spacenet(c, s, c->space[fine ? 1 : 0][0], raw, nullptr, nullptr, st);
+      rc = run_spacenet(c, s, c->space[fine ? 1 : 0][0], raw, nullptr, nullptr, st, -1, fuse ? &f : nullptr);
       if (rc) return rc;
       continue;
     }
@@ -502,7 +517,8 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     if (rc) return rc;
     s.mode = SRC_XYZ;
     s.pos = c->xyz;
-    rc = run_spacenet(c, s, c->space[fine ? 1 : 0][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
+    rc = run_spacenet(c, s, c->space[fine ? 1 : 0][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1,
+                      fuse ? &f : nullptr);
     if (rc) return rc;
   }
   return STNERF_OK;
@@ -564,10 +580,29 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
     }
     // NOTE: the workspace t arrays are laid out with the *capacity* sample counts as layer stride but the
     // per-ray stride is the live n1 / S2, so a ray's samples stay contiguous.
-    rc = run_nets(c, rch, n, ray_stride, false, n1, st, chunk_slot);
+    // Coarse-pass fusion: with a tensor-core mode and n1 = 64 the SpaceNet kernel composites and resamples every shown layer in
+    // its spare warps (mlp_tc.cuh: FuseCoarse).  The stand-alone kernel is then only needed for the merged coarse image (when
+    // coarse images are wanted), for the zero pixels of missed rays, and for the resampling of hit-but-hidden layers.
+    const bool fuse = n2 > 0 && c->precision != STNERF_PREC_FP32_SIMT && tc_can_fuse_coarse(n1, n2) && !c->no_fuse;
+    unsigned fused_layers = 0;
+    bool hidden_any = false;
+    for (int i = 0; i < l; ++i) {
+      if (i == 0 || c->scene.shown[i]) fused_layers |= fuse ? (1u << i) : 0u;
+      else hidden_any = true;
+    }
+    FuseCoarse ft;
+    memset(&ft, 0, sizeof(ft));
+    if (fuse) {
+      ft.n1 = n1; ft.n2 = n2; ft.u = u ? u + c0 * n2 : nullptr; ft.seed = seed; ft.idmap = c->idmap; ft.ray_base = c0;
+      ft.n_total = N; ft.pixels = out.pixels; ft.near_plane = c->dscene.near_plane; ft.thr = c->dscene.thr_layer;
+      ft.boarder = c->dscene.boarder; ft.apply_thr = c->dscene.apply_thr;
+    }
+    rc = run_nets(c, rch, n, ray_stride, false, n1, st, chunk_slot, fuse ? &ft : nullptr, /*want_raw=*/!fuse || out.coarse != nullptr,
+                  out.coarse, 5 * N);
     if (rc) return rc;
     CompositeArgs a;
     memset(&a, 0, sizeof(a));
+    a.skip_layers = fused_layers;
     a.t = c->t_coarse; a.t_layer_stride = R * c->cap_n1;
     a.raw = c->raw_coarse; a.raw_layer_stride = R * c->cap_n1 * 4;
     a.mask = mask; a.mask_layer_stride = mask_ls;
@@ -575,7 +610,7 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
     a.t_fine = c->t_fine; a.tf_layer_stride = R * c->cap_s2;
     a.out = out.coarse; a.pixel_layout = out.pixels; a.n_total = N; a.ray_base = c0; a.n = n;
     a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed; a.idmap = c->idmap;
-    {
+    if (!fuse || out.coarse != nullptr || hidden_any) {
       ProfScope ps(c, 3, (double)n, -1, 1, st);
       rc = launch_composite_pass(a, c->dscene, l, st);
       if (rc) return rc;
@@ -812,6 +847,11 @@ int stnerf_set_ray_ids(stnerf_handle c, int64_t base, int32_t width, int64_t row
 int stnerf_selftest_umma(float* max_err_host) {
   if (!max_err_host) return STNERF_EINVAL;
   return tc_selftest(max_err_host);
+}
+
+int stnerf_selftest_umma_accum(int reps, float* max_err_host, float* mean_signed_rel_err_host) {
+  if (!max_err_host || !mean_signed_rel_err_host || reps < 1 || reps > 4096) return STNERF_EINVAL;
+  return tc_selftest_accum(reps, max_err_host, mean_signed_rel_err_host);
 }
 
 int stnerf_selftest_umma_pair(float* max_err_host) {

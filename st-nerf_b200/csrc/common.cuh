@@ -167,6 +167,7 @@ struct CompositeArgs {
   float* t_fine;           // out (coarse pass with n2 > 0): [layer][ray][n1+n2]
   long long tf_layer_stride;
   float* out;              // images of this pass: [img][5*n_total], or null (coarse pass: resampling only, no images)
+  unsigned skip_layers;    // bit i: layer i's own image + resampling were produced elsewhere (fused SpaceNet kernel): gather only
   int pixel_layout;        // 0: plane = rgb (N,3) | depth (N) | acc (N);  1: plane = (N,5) pixel-interleaved
   long long n_total;       // rays in the whole call (plane geometry)
   long long ray_base;      // first ray of this chunk within the call

@@ -4,8 +4,10 @@
 // sort-merge of modeling/layered_rfrender.py:425-448 (coarse) / :587-606 (fine).  fp32, compiled with
 // -fmad=false so every product/sum rounds like the separate ATen ops of the reference.  Scans use warp
 // shuffles (tree order), so results agree with torch.cumprod / cumsum to a few ulp, not bit for bit.
+#include <algorithm>
 #include <math_constants.h>
 #include "common.cuh"
+#include "resample.cuh"
 
 namespace stnerf {
 
@@ -182,16 +184,18 @@ struct PassSmem {
 
 __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-static PassSmem pass_layout(int l, int S, int n2) {
+static PassSmem pass_layout(int l, int S, int n2, bool regs) {
   PassSmem L;
   const int tot = l * S;
   L.off_sig = tot;
   L.off_w = 2 * tot;
-  L.off_cdf = L.off_w + (n2 > 0 ? S : 0);
+  L.off_cdf = L.off_w + ((n2 > 0 && !regs) ? S : 0);      // the register-resident path keeps the weights in registers ...
   L.off_sort = L.off_cdf + (n2 > 0 ? S : 0);
   int sf = (tot + 1) / 2;                     // merge order: one uint16 per sample
-  if (n2 > 0 && next_pow2(S + n2) > sf) sf = next_pow2(S + n2);
-  if (n2 > 0 && S + next_pow2(n2) > sf) sf = S + next_pow2(n2);
+  if (!regs) {                                // ... and sorts / merges there too: no sort area beyond the merge order
+    if (n2 > 0 && next_pow2(S + n2) > sf) sf = next_pow2(S + n2);
+    if (n2 > 0 && S + next_pow2(n2) > sf) sf = S + next_pow2(n2);
+  }
   L.sort_floats = sf;
   L.per_warp_floats = (L.off_sort + sf + 3) & ~3;
   return L;
@@ -200,6 +204,9 @@ static PassSmem pass_layout(int l, int S, int n2) {
 constexpr int ORDER_K_BITS = 9;               // STNERF_MAX_S = 512 samples per list, STNERF_MAX_LAYERS = 8 lists
 static_assert(STNERF_MAX_S <= (1 << ORDER_K_BITS) && STNERF_MAX_LAYERS <= (1 << (16 - ORDER_K_BITS)), "merge order code is 16 bits");
 
+// NT, NZ > 0: the coarse pass' per-layer composite + resampling runs register-resident (resample.cuh: NT = ceil(n1/32) depth slots
+// and NZ = pow2 >= ceil(n2/32) new-depth slots per lane); NT == 0: generic shared-memory path (fine pass, unusual sample counts).
+template <int NT, int NZ>
 __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scene, int n_layers, const PassSmem L) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -225,6 +232,8 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
     int n_m = 0;                                  // entries gathered for the merged composite
     unsigned slot_layers = 0;                     // 4 bits per gathered list: which layer it is
     bool all_asc = true;                          // every gathered list is non-decreasing (always true for fine passes)
+    float single[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // pixel of the background layer's own composite (reused when it is the only list)
+    bool have_single = false;
     for (int i = 0; i < n_layers; ++i) {
       float* oimg = a.out ? a.out + (size_t)(1 + i) * plane : nullptr;
       const bool hit = (i == 0) || (a.mask[i * a.mask_layer_stride + r] != 0);
@@ -263,10 +272,49 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
         s_sig[off + k] = sg;
       }
       __syncwarp();
+      const bool done_elsewhere = (a.skip_layers >> i) & 1u;       // per-layer image + resampling produced by the fused SpaceNet kernel
+      if (done_elsewhere) {
+        all_asc = all_asc && warp_is_ascending(s_t + off, S, lane);
+        n_m += S;
+        continue;
+      }
+      const bool want_w = (!fine) && n2 > 0;
+      if (NT > 0 && !fine) {
+        // register-resident per-layer composite + hierarchical resampling of this layer (layered_rfrender.py:435-463)
+        constexpr int NTr = NT > 0 ? NT : 1, NZr = NZ > 0 ? NZ : 1;
+        float tr[NTr], sr[NTr];
+#pragma unroll
+        for (int q = 0; q < NTr; ++q) {
+          const int k = q * 32 + lane;
+          tr[q] = k < S ? s_t[off + k] : 0.f;
+          sr[q] = k < S ? s_sig[off + k] : 0.f;
+        }
+        const float* up = a.u ? a.u + i * a.u_layer_stride + r * n2 : nullptr;
+        const uint64_t seed = a.seed;
+        const unsigned long long gid = a.idmap(rg);
+        rs::LayerOut lo;
+        rs::composite_resample_ray<NTr, NZr>(
+            tr, sr, S, want_w ? n2 : 0, boarder,
+            [rp, shown, lane](int q) {
+              if (!shown) return make_float3(0.5f, 0.5f, 0.5f);
+              const float4 v = __ldg(rp + q * 32 + lane);
+              return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
+            },
+            [up, seed, i, gid](int j) { return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, gid, (uint32_t)j); },
+            s_cdf, want_w ? a.t_fine + i * a.tf_layer_stride + r * (S + n2) : nullptr, lane, lo);
+        write_pixel(oimg, rg, a.n_total, pixels, lo.pix, lane);
+        if (i == 0) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) single[q] = lo.pix[q];
+          have_single = true;
+        }
+        all_asc = all_asc && warp_is_ascending(s_t + off, S, lane);
+        n_m += S;
+        continue;
+      }
       const bool asc = warp_is_ascending(s_t + off, S, lane);
       all_asc = all_asc && asc;
       float o5[5];
-      const bool want_w = (!fine) && n2 > 0;
       // a hidden layer contributes sigmoid(0) colours with zero weight (its network output is never read)
       composite_run(S, [off](int j) { return off + j; },
                     [rp, shown](int j) {
@@ -276,6 +324,11 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
                     },
                     s_t, s_sig, boarder, 0.f, false, want_w ? s_w : nullptr, lane, o5);
       write_pixel(oimg, rg, a.n_total, pixels, o5, lane);
+      if (i == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) single[q] = o5[q];
+        have_single = true;
+      }
       __syncwarp();
       if (want_w) {
         // hierarchical resampling of this layer (layered_rfrender.py:459-463)
@@ -319,6 +372,13 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
     // ---- merged composite over every hit layer's samples, ordered by (t, cat index)  (:425-448 / :587-606)
     if (a.out != nullptr) {
       const int n_lists = n_m / S;
+      // One list only (the ray hits nothing but the background) and no sample in front of the near plane: the merged composite is
+      // the per-layer composite of that list, operation for operation -- its pixel was just computed (kept in `single`).
+      if (n_lists == 1 && have_single && !(fine && s_t[0] < near_p) && all_asc) {
+        write_pixel(a.out, rg, a.n_total, pixels, single, lane);
+        __syncwarp();
+        continue;
+      }
       if (all_asc) {
         // every list is sorted: the stable (t, cat index) order is a rank computation -- position of sample (h,k) =
         // k + #(samples of earlier lists with t' <= t) + #(samples of later lists with t' < t)
@@ -366,25 +426,43 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
   }
 }
 
-int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_layers, cudaStream_t st) {
-  if (a.n <= 0) return STNERF_OK;
-  if (a.S > STNERF_MAX_S || n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
-  const PassSmem L = pass_layout(n_layers, a.S, a.fine ? 0 : a.n2);
+template <int NT, int NZ>
+static int launch_pass_t(const CompositeArgs& a, const DevScene& scene, int n_layers, const PassSmem& L, cudaStream_t st) {
   const size_t per_warp = (size_t)L.per_warp_floats * sizeof(float);
   // blocks of up to 8 warps, as many blocks per SM as shared memory allows (228 KB per SM, 1 KB reserved per block)
   int wpb = 8;
   while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
   if (per_warp * wpb > 200 * 1024) return STNERF_EINVAL;
   const size_t smem = per_warp * wpb;
-  STNERF_CUDA(cudaFuncSetAttribute(composite_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = composite_pass_kernel<NT, NZ>;
+  STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm * wpb > 64) per_sm = 64 / wpb;
   if (per_sm < 1) per_sm = 1;
   long long blocks = (a.n + wpb - 1) / wpb;
   if (blocks > 148LL * per_sm * 4) blocks = 148LL * per_sm * 4;
-  composite_pass_kernel<<<(int)blocks, wpb * 32, smem, st>>>(a, scene, n_layers, L);
+  kern<<<(int)blocks, wpb * 32, smem, st>>>(a, scene, n_layers, L);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
+}
+
+int launch_composite_pass(const CompositeArgs& a, const DevScene& scene, int n_layers, cudaStream_t st) {
+  if (a.n <= 0) return STNERF_OK;
+  if (a.S > STNERF_MAX_S || n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
+  const bool regs = !a.fine && a.S <= 128 && a.n2 <= 256;
+  const PassSmem L = pass_layout(n_layers, a.S, a.fine ? 0 : a.n2, regs);
+  if (regs) {
+    // coarse pass: register-resident per-layer composite + resampling, instantiated for the slot counts in use
+    const int nt = (a.S + 31) / 32, nzr = (std::max(a.n2, 1) + 31) / 32;
+    const int nz = nzr <= 1 ? 1 : nzr <= 2 ? 2 : nzr <= 4 ? 4 : 8;
+#define STNERF_PASS_CASE(T_, Z_) if (nt == T_ && nz == Z_) return launch_pass_t<T_, Z_>(a, scene, n_layers, L, st);
+    STNERF_PASS_CASE(1, 1) STNERF_PASS_CASE(1, 2) STNERF_PASS_CASE(1, 4) STNERF_PASS_CASE(1, 8)
+    STNERF_PASS_CASE(2, 1) STNERF_PASS_CASE(2, 2) STNERF_PASS_CASE(2, 4) STNERF_PASS_CASE(2, 8)
+    STNERF_PASS_CASE(3, 1) STNERF_PASS_CASE(3, 2) STNERF_PASS_CASE(3, 4) STNERF_PASS_CASE(3, 8)
+    STNERF_PASS_CASE(4, 1) STNERF_PASS_CASE(4, 2) STNERF_PASS_CASE(4, 4) STNERF_PASS_CASE(4, 8)
+#undef STNERF_PASS_CASE
+  }
+  return launch_pass_t<0, 0>(a, scene, n_layers, L, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

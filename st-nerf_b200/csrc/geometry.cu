@@ -224,7 +224,8 @@ __global__ void raygen_kernel(RayGenParams P, int W, int row0, int row_step, int
 int launch_raygen(const float* Kinv, const float* T, int H, int W, int row0, int row_step, int n_rows,
                   const float* fids, int n_fids, float* rays, int ray_stride, cudaStream_t st) {
   if (n_rows <= 0 || W <= 0) return STNERF_OK;
-  if (n_fids > STNERF_MAX_LAYERS || ray_stride < 6 + n_fids || row0 + (long long)(n_rows - 1) * row_step >= H)
+  // rows past H-1 are extrapolated pixel rows (one padding row for equal shard sizes, see stnerf_render_views)
+  if (n_fids > STNERF_MAX_LAYERS || ray_stride < 6 + n_fids || row0 >= H || row0 + (long long)(n_rows - 1) * row_step >= H + row_step)
     return STNERF_EINVAL;
   RayGenParams P;
   for (int i = 0; i < 9; ++i) P.kinv[i] = Kinv[i];

@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 #include <vector>
 #include "mlp_tc.cuh"
+#include "resample.cuh"
 
 namespace stnerf {
 
@@ -54,10 +55,13 @@ constexpr int SM_ENC = 8 * ABLOCK;           // 2 blocks: hi, lo (SpaceNet).  Mo
 constexpr int SM_RING = 10 * ABLOCK;
 constexpr int SM_MISC = SM_RING + NSTAGE * STAGE_BYTES;
 constexpr int MAX_STAGE = 8;                 // ring slots a kernel may use (CTA-pair mode: 8 half-size stages in the same 64 KB)
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 29, BAR_DEMPTY = 31;   // 33 barriers
-constexpr int MISC_TMEM = 272;
-constexpr int MISC_PART = 288;               // float[128][4]: head partial sums of column-half 1
-constexpr int SM_TOTAL = SM_MISC + MISC_PART + 2048;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 29, BAR_DEMPTY = 31,
+              BAR_RAWFULL = 33, BAR_RAWEMPTY = 34;                                                                // 35 barriers
+constexpr int MISC_TMEM = 280;
+constexpr int MISC_PART = 288;               // float[128][4]: head partial sums of column-half 1; with the coarse-pass fusion: the
+                                             // tile's final (rgb logits, sigma) rows, read by the compositing warps
+constexpr int MISC_CDF = MISC_PART + 2048;   // fused compositing warps: cdf / depth scratch, 2 x 64 floats
+constexpr int SM_TOTAL = SM_MISC + MISC_CDF + 512;
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
 // ---------------------------------------------------------------------------------------------------------
@@ -252,7 +256,7 @@ template <> struct Sched<NET_MOTION> {
   static constexpr int act_base = SM_ACT, enc_base = SM_ACT;
   static constexpr int N_THREADS = 320, EPI_W0 = 2, CTAS_PER_SM = 2;
   static constexpr int ring_base = 4 * ABLOCK, stage_bytes = 8192, misc_base = ring_base + NSTAGE * stage_bytes,
-                       smem_total = misc_base + MISC_PART + 2048;
+                       smem_total = misc_base + MISC_CDF;
   static constexpr int tmem_cols = 256, d_stride = 128;
   static constexpr bool ENC_ALIASES_ACT = true;
 #else
@@ -275,6 +279,7 @@ __host__ __device__ constexpr size_t stream_bytes_per_tile() {
 }
 
 struct TcParams {
+  FuseCoarse fuse;            // SpaceNet, coarse pass: per-layer compositing + resampling in the kernel's spare warps
   PointSrc src;
   const uint8_t* wstream;     // packed weight stream (hi/lo stages in consumption order)
   const float* aux;           // fp32: biases [8][256] | w_sigma[256] | b_sigma | w_out[3][128] | b_out[3]
@@ -534,6 +539,68 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// coarse-pass fusion: what the two spare warps of the SpaceNet kernel run (see FuseCoarse in mlp_tc.cuh)
+// ---------------------------------------------------------------------------------------------------------
+// Tile `tile` holds slots 2*tile and 2*tile+1 (a slot = one hit ray of this layer, 64 coarse samples = rows 64*j .. 64*j+63);
+// warp `j` composites slot 2*tile+j from the rows the epilogue warps left in `rows` (float4 per row: rgb logits, sigma).
+template <int NZ>
+__device__ __noinline__ void fused_composite_loop(const TcParams& P, const float* rows, float* cdf, uint32_t bar_full, uint32_t bar_empty,
+                                                  long long n_tiles, int j, int lane) {
+  const FuseCoarse& F = P.fuse;
+  const PointSrc& src = P.src;
+  const long long n_slots = src.count ? (long long)(*src.count) : src.n_slots;
+  const int n1 = 64, n2 = F.n2;
+  uint32_t n = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    mbar_wait(bar_full, n & 1);
+    const long long slot = tile * 2 + j;
+    if (slot < n_slots) {
+      const long long ray = src.hit ? (long long)src.hit[slot] : slot;
+      const float* tp = src.t + ray * n1;
+      const float4* rp = reinterpret_cast<const float4*>(rows) + j * 64;
+      float t[2], sg[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int k = s * 32 + lane;
+        const float tk = __ldg(tp + k);
+        float v = rp[k].w;
+        if (F.is_bkgd) {
+          if (tk < F.near_plane) v = 0.0f;                                     // layered_rfrender.py:422
+        } else {
+          if (tk < 0.0f) v = 0.0f;                                              // :414
+          if (F.apply_thr && v < F.thr) v = 0.0f;                               // :416-418
+        }
+        t[s] = tk;
+        sg[s] = v;
+      }
+      const float* up = F.u ? F.u + ray * n2 : nullptr;
+      const uint64_t seed = F.seed;
+      const uint32_t stream = 64u + (uint32_t)F.layer;
+      const unsigned long long gid = F.idmap(F.ray_base + ray);
+      rs::LayerOut lo;
+      rs::composite_resample_ray<2, NZ>(
+          t, sg, n1, n2, F.boarder,
+          [rp, lane](int s) {
+            const float4 v = rp[s * 32 + lane];
+            return make_float3(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v.x))), __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v.y))),
+                               __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v.z))));
+          },
+          [up, seed, stream, gid](int jj) { return up ? up[jj] : philox_uniform(seed, stream, gid, (uint32_t)jj); },
+          cdf, F.t_fine + ray * (n1 + n2), lane, lo);
+      if (F.img && lane < 5) {
+        const long long rg = F.ray_base + ray;
+        const float v = lane == 0 ? lo.pix[0] : lane == 1 ? lo.pix[1] : lane == 2 ? lo.pix[2] : lane == 3 ? lo.pix[3] : lo.pix[4];
+        if (F.pixels) F.img[rg * 5 + lane] = v;
+        else if (lane < 3) F.img[rg * 3 + lane] = v;
+        else F.img[(long long)lane * F.n_total + rg] = v;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
 // PAIR: the two CTAs of a cluster share ONE M = 256 accumulator (`cta_group::2`).  Each CTA still owns a 128-point tile -- its
@@ -542,7 +609,7 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 // weight traffic are halved.  Barriers the leader's MMA warp waits on collect arrivals from both CTAs (remote arrives);
 // `tcgen05.commit` multicasts to the same barrier in both CTAs.
 template <int NET, bool PAIR = false>
-__global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   using S = Sched<NET>;
   static_assert(!PAIR || NET == NET_SPACE, "the CTA-pair protocol is built for the SpaceNet schedule");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -576,6 +643,8 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), 1); mbar_init(BAR(BAR_WPEER + i), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(BAR(BAR_AREADY + i), N_ARRIVE);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_ARRIVE); }
+    mbar_init(BAR(BAR_RAWFULL), 4);          // the four epilogue warps that own the tile's final rows
+    mbar_init(BAR(BAR_RAWEMPTY), 2);         // the two compositing warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), S::tmem_cols); else tmem_alloc(smem_u32(tmem_slot), S::tmem_cols); }
@@ -692,6 +761,13 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
         }
       }
     }
+  } else if (NET == NET_SPACE && !PAIR && (warp == 2 || warp == 3)) {
+    // =============================== compositing warps (coarse-pass fusion) ===============================
+    if (P.fuse.on) {
+      float* cdf = reinterpret_cast<float*>(smem + S::misc_base + MISC_CDF) + (warp - 2) * 64;
+      if (P.fuse.n2 <= 128) fused_composite_loop<4>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane);
+      else fused_composite_loop<8>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane);
+    }
   } else if (warp >= S::EPI_W0) {
     // =============================== encoding + epilogue warps ===============================
     const int ew = warp - S::EPI_W0;            // 0..7
@@ -730,7 +806,8 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       __syncwarp();
       if (lane == 0) ARRIVE(BAR_AREADY + 4);
     }
-    for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
+    uint32_t tile_no = 0;                       // tiles this CTA has finished (phase of the fused compositing hand-off)
+    for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x, ++tile_no) {
       const long long nt = tile + gridDim.x;
       const bool have_next = in_range(nt);
       Pt nxt = cur;
@@ -857,19 +934,35 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             __syncwarp();
             if (lane == 0) ARRIVE(BAR_AREADY + 4);
           }
-          // combine the two column halves through shared memory
+          // combine the two column halves through shared memory.  With the coarse-pass fusion the tile's FINAL rows go to
+          // `s_part` for the compositing warps, so the half sums travel through the first activation block instead: every
+          // MMA of this tile has retired (d_full above) and the next writer of that block is this very warp group (layer-0
+          // epilogue of the next tile).
+          const bool fused = (NET == NET_SPACE) && !PAIR && P.fuse.on;
+          float* s_half = fused ? reinterpret_cast<float*>(smem + S::act_base) : s_part;
           if (hh == 1) {
-            s_part[row * 4 + 0] = dot3[0]; s_part[row * 4 + 1] = dot3[1]; s_part[row * 4 + 2] = dot3[2];
-            s_part[row * 4 + 3] = sig_dot;
+            s_half[row * 4 + 0] = dot3[0]; s_half[row * 4 + 1] = dot3[1]; s_half[row * 4 + 2] = dot3[2];
+            s_half[row * 4 + 3] = sig_dot;
           }
           epi_bar_sync();
+          if (fused && hh == 0) {
+            // the compositing warps must be done with the previous tile's rows (they have had a whole tile period)
+            if (tile_no > 0) mbar_wait(BAR(BAR_RAWEMPTY), (tile_no - 1) & 1);
+            const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
+            const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
+            const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
+            const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
+            reinterpret_cast<float4*>(s_part)[row] = make_float4(o0, o1, o2, sg);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_RAWFULL));
+          }
           if (hh == 0 && cur.out_index >= 0) {
-            const float o0 = dot3[0] + s_part[row * 4 + 0] + P.aux[AUX_BOUT + 0];
-            const float o1 = dot3[1] + s_part[row * 4 + 1] + P.aux[AUX_BOUT + 1];
-            const float o2 = dot3[2] + s_part[row * 4 + 2] + P.aux[AUX_BOUT + 2];
+            const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
+            const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
+            const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
             const int oi = cur.out_index;
             if (NET == NET_SPACE) {
-              const float sg = sig_dot + s_part[row * 4 + 3] + P.aux[AUX_BSIG];
+              const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
               if (P.raw) reinterpret_cast<float4*>(P.raw)[oi] = make_float4(o0, o1, o2, sg);
               if (P.rgb_out) { P.rgb_out[3 * (size_t)oi] = o0; P.rgb_out[3 * (size_t)oi + 1] = o1; P.rgb_out[3 * (size_t)oi + 2] = o2; }
               if (P.sigma_out) P.sigma_out[oi] = sg;
@@ -883,7 +976,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               }
             }
           }
-          epi_bar_sync();       // s_part is rewritten by the next tile
+          epi_bar_sync();       // the half sums are rewritten by the next tile
 #ifdef STNERF_TIMING
           tm.last_wait += tl1 - tl0; tm.last_epi += clock64() - tl1; tm.tiles += 1;
 #endif
@@ -978,7 +1071,7 @@ __global__ void __launch_bounds__(128) head_bias_kernel(PointSrc src, const floa
 // self-test: 128 x N x 64 fp16 UMMA (N = 256) through exactly the descriptors / swizzles / bulk copy / TMEM load used above
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bstages,
-                                                              float* __restrict__ D) {
+                                                              float* __restrict__ D, int reps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar = sbase + ABLOCK + 2 * STAGE_BYTES, bar2 = bar + 8;
@@ -1007,10 +1100,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     bulk_g2s(sbase + ABLOCK, Bstages, 2 * STAGE_BYTES, bar2);
     mbar_wait(bar2, 0);
     tc_fence_after();
-    for (int sub = 0; sub < 2; ++sub)
-      for (int ks = 0; ks < 2; ++ks)
-        umma_f16(tmem_base, make_desc_sw128(sbase + sub * 64 + ks * 32),
-                 make_desc_sw64(sbase + ABLOCK + sub * STAGE_BYTES + ks * 32), idesc_n(256), (sub | ks) ? 1u : 0u);
+    for (int rep = 0; rep < reps; ++rep)       // reps > 1: the same product accumulated again and again (accumulation probe)
+      for (int sub = 0; sub < 2; ++sub)
+        for (int ks = 0; ks < 2; ++ks)
+          umma_f16(tmem_base, make_desc_sw128(sbase + sub * 64 + ks * 32),
+                   make_desc_sw64(sbase + ABLOCK + sub * STAGE_BYTES + ks * 32), idesc_n(256), (rep | sub | ks) ? 1u : 0u);
     umma_commit(bar);
   }
   mbar_wait(bar, 0);
@@ -1259,10 +1353,14 @@ int tc_pack_motionnet(TcNet& net, const float* p) {
 }
 
 // D = A * B^T for random A (128x64, rounded to fp16), B (256x64) through the tensor-core path; max |D - reference|.
-int tc_selftest(float* max_err_host) {
+// reps > 1 (accumulation probe): all-positive operands, the product accumulated `reps` times into the same TMEM accumulator
+// (4*reps MMAs of K=16); reports the max and the MEAN SIGNED relative error against the fp64 sum -- a negative mean that grows
+// with reps is the signature of round-toward-zero accumulation inside the tensor core.
+int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host) {
   std::vector<float> Af(128 * 64), Bf(256 * 64);
   uint32_t s = 12345u;
-  auto rnd = [&s]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  const bool probe = reps > 1;
+  auto rnd = [&s, probe]() { s = s * 1664525u + 1013904223u; const float v = ((s >> 8) & 0xFFFF) / 65536.0f; return probe ? 0.5f + 0.5f * v : v - 0.5f; };
   for (auto& v : Af) v = __half2float(__float2half_rn(rnd()));
   for (auto& v : Bf) v = __half2float(__float2half_rn(rnd()));
   std::vector<uint8_t> stages(2 * STAGE_BYTES, 0);
@@ -1280,22 +1378,27 @@ int tc_selftest(float* max_err_host) {
   STNERF_CUDA(cudaMemcpy(dB, stages.data(), stages.size(), cudaMemcpyHostToDevice));
   const int smem = ABLOCK + 2 * STAGE_BYTES + 64;
   STNERF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD);
+  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, reps);
   STNERF_LAUNCH_CHECK();
   STNERF_CUDA(cudaDeviceSynchronize());
   std::vector<float> D(128 * 256);
   STNERF_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
   float worst = 0.f;
+  double signed_rel = 0.0;
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < 256; ++n) {
       double ref = 0;
       for (int k = 0; k < 64; ++k) ref += (double)Af[m * 64 + k] * Bf[n * 64 + k];
-      worst = fmaxf(worst, fabsf((float)ref - D[m * 256 + n]));
+      ref *= reps;
+      worst = fmaxf(worst, fabsf((float)(ref - (double)D[m * 256 + n])));
+      if (ref != 0.0) signed_rel += ((double)D[m * 256 + n] - ref) / fabs(ref);
     }
   *max_err_host = worst;
+  if (mean_signed_rel_host) *mean_signed_rel_host = (float)(signed_rel / (128.0 * 256.0));
   return STNERF_OK;
 }
+int tc_selftest(float* max_err_host) { return tc_selftest_accum(1, max_err_host, nullptr); }
 
 // The same for the CTA-pair protocol: 256 x 256 x 64.
 int tc_selftest_pair(float* max_err_host) {
@@ -1362,8 +1465,10 @@ static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   return STNERF_OK;
 }
 
+bool tc_can_fuse_coarse(int n1, int n2) { return SPACE_CTA_PAIR == 0 && n1 == 64 && n2 >= 1 && n2 <= 256; }
+
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, int precision, float* cbuf, float* raw,
-                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st) {
+                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse) {
   if (!net.blob || !net.w_tail) return STNERF_ENOWEIGHTS;
   if (!cbuf) return STNERF_EINVAL;
   // per-slot bias of rgb_net.1 (dir/time part), then the fused MLP
@@ -1381,6 +1486,10 @@ int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, 
   P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED;
   P.single_last = precision == STNERF_PREC_TC_MIXED;
   P.raw = raw; P.rgb_out = rgb_out; P.sigma_out = sigma_out; P.lerp_force = 0;
+  if (fuse && fuse->on) {
+    if (src.mode == SRC_EXPLICIT || src.S != 64 || !tc_can_fuse_coarse(fuse->n1, fuse->n2) || !fuse->t_fine) return STNERF_EINVAL;
+    P.fuse = *fuse;
+  }
   return launch_tc<NET_SPACE>(P, num_sms, st);
 }
 

@@ -331,7 +331,11 @@ def reference_job(case: dict, rays, jit, u, sd=None, **extra) -> dict:
 
 
 def run_reference_job(job: dict, workers: int = 1, threads: int = 0) -> dict:
-    """Run the unmodified reference on `job` in a separate process (oracle/run_reference.py); returns its result dict."""
+    """Run the unmodified reference on `job` in a separate process (oracle/run_reference.py); returns its result dict.
+    threads = 0: min(16, cores) per worker (the reference's eager fp32 ops stop scaling there; 128 threads on a few hundred
+    rays are slower than 8)."""
+    if threads <= 0:
+        threads = min(16, os.cpu_count() or 1) * max(1, workers)
     import subprocess
     import tempfile
     d = tempfile.mkdtemp(prefix="stnerf_refcall_")

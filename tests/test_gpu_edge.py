@@ -120,3 +120,38 @@ def test_c_abi_rejects_bad_arguments():
     assert lib.stnerf_render(*args(64, 128, 8)) == -1            # ray row narrower than 6 + l
     torch.cuda.synchronize()
     r.close()
+
+
+def test_coarse_fusion_is_not_observable(monkeypatch):
+    """The coarse-pass fusion (per-layer compositing + resampling inside the SpaceNet kernel's spare warps, mlp_tc.cuh:
+    FuseCoarse) and the stand-alone compositing kernel run the same arithmetic (csrc/resample.cuh): every output of forward() --
+    coarse and fine images of every layer, masks -- is bit-identical with the fusion switched off (STNERF_NO_FUSE=1), with
+    injected uniforms and with the in-kernel Philox stream, for 64+128 and 64+192 samples and with a hidden layer."""
+    for name, n2, hidden in (("tkd_64_128", 128, []), ("walk_L4_64_128", 192, [2])):
+        case = dict(C.CASES[name], n2=n2, hidden=hidden)
+        if C.state_dict_for(case) is None:
+            pytest.skip("checkpoint copy absent")
+        rays = C.rays_for(case).cuda()
+        jit, _ = C.uniforms_for(case)
+        rs = np.random.RandomState(5)
+        u = torch.from_numpy(rs.random_sample((case["L"] + 1, case["n_rays"], n2)).astype(np.float32)).clamp_(max=0.99999994)
+        outs = {}
+        for fused in (True, False):
+            if fused:
+                monkeypatch.delenv("STNERF_NO_FUSE", raising=False)
+            else:
+                monkeypatch.setenv("STNERF_NO_FUSE", "1")
+            model = build_case_model(case, "exact")
+            res = []
+            for inject in (True, False):
+                if inject:
+                    model.inject_uniforms(jit.cuda(), u.cuda())
+                model.seed = 41
+                with torch.no_grad():
+                    o = model(rays, None, None, density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+                res.append(C.flatten_outputs(*o))
+            outs[fused] = res
+            del model
+        for a, b in zip(outs[True], outs[False]):
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (name, k, float(np.abs(a[k].astype(np.float64) - b[k]).max()))
