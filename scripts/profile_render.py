@@ -17,23 +17,39 @@ ap.add_argument("--precision", default="exact")
 ap.add_argument("--calls", type=int, default=2)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--workload", default="taekwondo2", choices=list(B.WORKLOADS))
+ap.add_argument("--fine-only", action="store_true", help="the renderer fast path: no coarse images (coarse rgb/sigma never reach HBM)")
 a = ap.parse_args()
-sd, _ = B.load_weights()
-bkgd, frames, cams = B.scene_setup()
-m = modeling.build_layered_model(make_cfg(B.LAYERS, B.N1, B.N2, True, a.precision, a.chunk))
+wl = B.WORKLOADS[a.workload]
+H, W, N1, N2 = wl["H"], wl["W"], wl["n1"], wl["n2"]
+sd, _ = B.load_weights(wl)
+bkgd, frames, cams = B.scene_setup(wl)
+m = modeling.build_layered_model(make_cfg(wl["layers"], N1, N2, wl["space_time"], a.precision, a.chunk))
 m.load_state_dict(sd); m.set_bkgd_bbox(bkgd); m.set_bboxes(frames)
+m.near = wl["near"]
 dev = torch.device("cuda", 0)
 nat = m._ensure_native(dev)
-nat.set_scene(m._resolve_scene(torch.tensor(B.FRAME_IDS), 0.0, 0.0))
+scene = m._resolve_scene(torch.tensor(wl["frame_ids"]), wl["thr"][0], wl["thr"][1])
+nat.set_scene(scene)
 K, T = cams[0]
-rows = (a.rays + B.W - 1) // B.W
-rays = ops.generate_rays(K, T, B.H, B.W, frame_ids=B.FRAME_IDS, row0=(B.H - rows) // 2, n_rows=rows)[:a.rays].contiguous()
+rows = (a.rays + W - 1) // W
+rays = ops.generate_rays(K, T, H, W, frame_ids=wl["frame_ids"], row0=(H - rows) // 2, n_rows=rows)[:a.rays].contiguous()
+view = nat.make_view(K, T, wl["frame_ids"], scene, 7)
+
+
+def call(seed):
+    if a.fine_only:      # same rows through the views API with coarse_images = NULL
+        nat.render_views([view], H, W, N1, N2, row0=(H - rows) // 2, row_step=1, n_rows=rows)
+    else:
+        nat.render(rays, N1, N2, seed=seed)
+
+
 for i in range(a.warm):
-    nat.render(rays, B.N1, B.N2, seed=i + 1)
+    call(i + 1)
 torch.cuda.synchronize()
 nat.profile_begin()
 for i in range(a.calls):
-    nat.render(rays, B.N1, B.N2, seed=100 + i)
+    call(100 + i)
 prof = nat.profile_end()
 print(json.dumps({"lib": os.environ.get("STNERF_B200_LIB", "default"), "rays": rays.shape[0], "calls": a.calls, "chunk": a.chunk,
                   "ms_per_call": {k: round(v["ms"] / a.calls, 3) for k, v in prof.items()},

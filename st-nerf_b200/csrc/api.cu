@@ -622,7 +622,7 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
       a.raw = c->raw_fine; a.raw_layer_stride = R * c->cap_s2 * 4;
       a.u = nullptr; a.t_fine = nullptr;
       a.out = out.fine;
-      a.S = S2; a.n2 = 0; a.fine = 1;
+      a.S = S2; a.n2 = 0; a.fine = 1; a.skip_layers = 0;
       ProfScope ps(c, 3, (double)n, -1, 1, st);
       rc = launch_composite_pass(a, c->dscene, l, st);
       if (rc) return rc;

@@ -9,7 +9,7 @@ import torch
 
 import cases as C
 from oracle import stnerf_oracle as O
-from tests_support import make_cfg
+from tests_support import build_case_model, make_cfg
 
 pytestmark = pytest.mark.gpu
 

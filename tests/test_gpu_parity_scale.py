@@ -14,13 +14,19 @@ reference amplify such differences without bound:
     fraction of the bin, and the fine network is steep there;
   * `modeling/layered_rfrender.py:416-418, 538-547, 564-566`: densities below a threshold are zeroed (walking: 20 / 0.8).
 Attribution, per ray over the gate (reference re-run out of process from the archive packed by oracle/stash_reference.py):
-the reference's OWN pixel must move by more than a quarter of the gate under perturbations of the size of the measured
-disagreement -- every density scaled by 1 +- 3e-5 (coherent, like the truncation bias; this also moves densities across the
-thresholds), or the coarse weights it resamples from perturbed by a random relative +-1e-5 (four seeds) -- while at least
-95 % of ordinary rays move by less than that under the same perturbations.  A ray over the gate on which the reference is
-stable is a bug and fails the test.  Reported besides (not asserted): for how many of those rays the reference, re-run with
-ITS fine depths replaced by the ones the B200 path chose, reproduces the B200 pixel within 1e-3 (difference = sample
-placement only; the rest crossed a density threshold in the fine pass).
+  A  the reference, re-run with ITS fine depths replaced by the ones the B200 path chose, reproduces the B200 pixel (measured:
+     to ~1e-6; asserted: a quarter of the gate) -- fine networks, thresholds and compositing agree exactly, the whole difference
+     is where the fine samples were placed; and those placements are the reference's own up to its conditioning: every fine
+     depth matches the reference's within the shift a cdf change of 1e-4 produces (`|dz| * denom / bin_width <= 1e-4`;
+     samples on the `denom < 1e-5` branch point excepted).  A 1.5e-4 shift of ONE sample is enough to flip a pixel by 3e-2 when
+     the fine density there sits on a threshold (walking 6-layer, ray 3608).
+  or
+  C  the reference's OWN pixel moves by more than a quarter of the gate under perturbations of the size of the measured
+     disagreement: every density scaled by 1 +- 3e-5 (coherent, like the truncation bias; this also moves densities across the
+     thresholds), or the coarse weights it resamples from perturbed by a random relative +-1e-5 (four seeds), while at least
+     95 % of ordinary rays move by less than that.
+A ray over the gate with neither is a bug and fails the test.  `mixed` (single fp16 pass on the colour-only layer, opt-in)
+is held to the same rules except that its colour-only error on per-layer images may reach 2.5e-3 on at most 0.05 % of rays.
 """
 import json
 import os
@@ -74,7 +80,27 @@ def _z_from_merged(t_fine, t_coarse):
     return t_fine[keep]
 
 
-def attribute_outliers(case, model, rays, jit, u, idx, flat_full):
+BAND = 16 * 2.0 ** -24               # cumsum round-off reach around the 1e-5 branch point of utils/sample_pdf.py:59
+CDF_EPS = 1e-4                       # agreement of the coarse cdfs the placement check allows for
+
+
+def _placement_implied_dcdf(z_gpu, z_ref, denom, lo, hi):
+    """max over the samples of one (ray, layer) of |dz| * denom / bin_width: the cdf difference that explains the shift."""
+    order = np.argsort(z_ref, kind="stable")
+    z_ref, denom, lo, hi = z_ref[order], denom[order], lo[order], hi[order]
+    band = np.abs(denom - 1e-5) <= BAND
+    near_band = band.copy()
+    for sft in (1, 2):                   # a moved branch-point sample shifts its neighbours' sorted positions
+        near_band[sft:] |= band[:-sft]
+        near_band[:-sft] |= band[sft:]
+    width = np.maximum(np.abs(hi - lo), 1e-12)
+    den_eff = np.where(denom < 1e-5, 1.0, denom)
+    implied = np.abs(z_gpu - z_ref) * den_eff / width
+    ok = ~near_band
+    return float(implied[ok].max()) if ok.any() else 0.0
+
+
+def attribute_outliers(case, model, rays, jit, u, idx, flat_full, mixed=False):
     """Criteria A / B / C for the rays `idx`.  Returns a report dict; raises AssertionError on an unattributed ray."""
     l, n1, n2 = case["L"] + 1, case["n1"], case["n2"]
     idx = np.asarray(sorted(set(int(i) for i in idx)))[:MAX_ATTRIBUTED]
@@ -106,17 +132,37 @@ def attribute_outliers(case, model, rays, jit, u, idx, flat_full):
         variants += [dict(perturb_seed=sd_, perturb_rel=PERTURB_REL) for sd_ in SEEDS]
         var = C.run_reference_job(C.reference_job(case, r_s, j_s, u_s, variants=variants))["variants"]
         _cache[key] = (base, var)
-    ref = base["flat"]
+    ref, rec = base["flat"], base["record"]
     on_b200_depths = _err(sub, var[0]["flat"], l)
     score = np.max([_err(v["flat"], ref, l) for v in var[1:]], axis=0)       # how far the reference itself moves
+    implied = np.zeros(n)
     for r in range(no):
-        assert score[r] > UNSTABLE, "ray %d is over the gate but the reference is stable there (moves %.2e under the perturbations)" % (
-            int(idx[r]), score[r])
+        for i in range(l):
+            if ref["ray_mask.%d" % i][r] and not (i > 0 and i in case.get("hidden", [])):
+                implied[r] = max(implied[r], _placement_implied_dcdf(_z_from_merged(tf[i][r], tc[i][r]), rec["z"][i][r], rec["denom"][i][r],
+                                                                      rec["bin_lo"][i][r], rec["bin_hi"][i][r]))
+    dump = os.path.join(C.ROOT, "gpurun_out")
+    if os.path.isdir(dump):              # raw material for offline analysis (scratch, not asserted on)
+        np.savez_compressed(os.path.join(dump, "attrib_%s_%s.npz" % (case["name"], model.precision)), sel=sel.numpy(), n_out=no, score=score,
+                            on_b200_depths=on_b200_depths, implied=implied, **{"tc%d" % i: tc[i] for i in range(l)},
+                            **{"tf%d" % i: tf[i] for i in range(l)}, **{"sub." + k: v for k, v in sub.items()}, **{"ref." + k: v for k, v in ref.items()})
+    labels, unattributed = [], []
+    for r in range(no):
+        A = on_b200_depths[r] <= UNSTABLE and implied[r] <= CDF_EPS
+        Cc = score[r] > UNSTABLE
+        labels.append("placement" if A else ("unstable" if Cc else "unattributed"))
+        if not (A or Cc):
+            unattributed.append((int(idx[r]), float(_err(sub, ref, l)[r]), float(on_b200_depths[r]), float(score[r])))
+    if mixed:        # colour precision of the single-pass layer: small, rare, colour only (acc / depth untouched by construction)
+        assert len(unattributed) <= 5e-4 * rays.shape[0] and all(e[1] <= 2.5e-3 for e in unattributed), unattributed
+    else:
+        assert not unattributed, "rays over the gate that are neither placement-explained nor unstable in the reference: %s" % unattributed
     assert (score[no:] < UNSTABLE).mean() >= 0.95, "ordinary rays are unstable too: %s" % np.sort(score[no:])[-5:]
-    return {"rays_attributed": int(no),
-            "reference_move_under_perturbations": {"outliers_min": float(score[:no].min()), "outliers_median": float(np.median(score[:no])),
-                                                   "controls_median": float(np.median(score[no:])), "controls_p95": float(np.sort(score[no:])[int(0.95 * (n - no))])},
-            "outliers_reproduced_by_reference_on_b200_depths": int((on_b200_depths[:no] <= GATE).sum())}
+    return {"rays_attributed": int(no), "labels": {k: labels.count(k) for k in sorted(set(labels))},
+            "max_err_of_reference_on_b200_depths_vs_b200": float(on_b200_depths[:no][[lb == "placement" for lb in labels]].max()) if "placement" in labels else None,
+            "max_implied_cdf_difference_of_placements": float(implied[:no].max()),
+            "reference_move_under_perturbations": {"outliers_median": float(np.median(score[:no])), "controls_median": float(np.median(score[no:])),
+                                                   "controls_p95": float(np.sort(score[no:])[int(0.95 * (n - no))])}}
 
 
 @pytest.mark.gpu
@@ -146,7 +192,7 @@ def test_parity_at_scale_vs_reference(name):
         dd = np.abs(flat["fine_mixed.depth"] - gold["fine_mixed.depth"])[ok]
         assert (dd <= 2e-2 + 2e-3 * np.abs(gold["fine_mixed.depth"][ok])).all()
         if out.size:
-            rep["attribution"] = attribute_outliers(case, model, rays, jit, u, out, flat)
+            rep["attribution"] = attribute_outliers(case, model, rays, jit, u, out, flat, mixed=(prec == "mixed"))
         report[prec] = rep
         del model
     dst = os.path.join(C.ROOT, "gpurun_out")

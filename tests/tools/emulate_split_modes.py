@@ -13,15 +13,16 @@ from oracle import stnerf_oracle as O
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 torch.set_num_threads(min(32, os.cpu_count() or 1))
-sd, data = B.load_weights()
-bkgd, frames, cams = B.scene_setup()
+WL = WL["W"]ORKLOADS["taekwondo2"]
+sd, data = B.load_weights(WL)
+bkgd, frames, cams = B.scene_setup(WL)
 K, T = cams[3]
-full = O.generate_rays(K, T, B.H, B.W)
-idx = torch.linspace(0, B.H * B.W - 1, n).long()
-rays = torch.cat([full[idx], torch.tensor(B.FRAME_IDS)[None].expand(n, -1)], 1).contiguous()
+full = O.generate_rays(K, T, WL["H"], WL["W"])
+idx = torch.linspace(0, WL["H"] * WL["W"] - 1, n).long()
+rays = torch.cat([full[idx], torch.tensor(WL["frame_ids"])[None].expand(n, -1)], 1).contiguous()
 g = torch.Generator().manual_seed(11)
-jit = torch.rand((3, n, B.N1), generator=g); u = torch.rand((3, n, B.N2), generator=g)
-sc = O.resolve_scene(frames, bkgd, B.FRAME_IDS, None, None)
+jit = torch.rand((3, n, WL["n1"]), generator=g); u = torch.rand((3, n, WL["n2"]), generator=g)
+sc = O.resolve_scene(frames, bkgd, WL["frame_ids"], None, None)
 sc.update(scale=None, shift=None, shown=[True] * 3, near=0.0, alpha=1.0, boarder=1e10)
 nets = O.split_state_dict(sd, 2)
 
@@ -38,7 +39,7 @@ def run():
     outs = []
     with torch.no_grad():
         for c0 in range(0, n, 2048):
-            w = O.render(nets, sc, rays[c0:c0 + 2048], B.N1, B.N2, jit[:, c0:c0 + 2048], u[:, c0:c0 + 2048],
+            w = O.render(nets, sc, rays[c0:c0 + 2048], WL["n1"], WL["n2"], jit[:, c0:c0 + 2048], u[:, c0:c0 + 2048],
                          density_threshold=0.0, bkgd_density_threshold=0.0)
             outs.append(w["fine_mixed"][0])
     return torch.cat(outs, 0)
