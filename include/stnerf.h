@@ -104,6 +104,12 @@ int stnerf_load_spacenet(stnerf_handle h, int layer, int fine, const float* blob
 int stnerf_load_motionnet(stnerf_handle h, int layer, const float* blob_host, size_t n_floats);
 
 int stnerf_set_scene(stnerf_handle h, const stnerf_scene* scene_host);
+/* Per-frame boxes for rays that carry their OWN frame id: the 7-column rays of a mixed-frame batch (training / evaluation),
+ * `bboxes = self.bboxes.index_select(0, rays_frame_id - 1)` (modeling/layered_rfrender.py:193).  table_host:
+ * [n_frames][l][2][3] = (min, max) corner of every layer's box at every frame AFTER the scale / shift edits (:230-242), entry
+ * [f][0] = the background box.  With a table set and scene.shared_frame_id = 1, ray r is clipped against row
+ * (int)rays[r][6] - 1 (ids outside [1, n_frames] are clamped; the reference raises).  n_frames = 0 removes the table.      */
+int stnerf_set_box_table(stnerf_handle h, const float* table_host, int n_frames);
 
 /* ---- the hot path: LayeredRFRender.forward (layered_rfrender.py:141-734), BBOX sampling ---------------- */
 /* rays: (n_rays, ray_stride) fp32, columns [o(3), d(3), frame_id_layer0 .. frame_id_layer(l-1)]

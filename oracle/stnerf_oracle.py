@@ -109,11 +109,11 @@ def ray_box_intersect(o: torch.Tensor, d: torch.Tensor, bmin: torch.Tensor, bmax
     col = 0
     for axis in range(3):
         a1, a2 = [a for a in range(3) if a != axis]
-        for face in (bmin[axis], bmax[axis]):
+        for face in (bmin[..., axis], bmax[..., axis]):               # bmin / bmax: (3,) one box, or (N,3) a box per ray
             t = (face - o[:, axis]) / (d[:, axis] + eps)                # :17-22
             p = t[:, None] * d + o                                      # :27-32 (mul then add)
-            ok = (p[:, a1] >= bmin[a1]) & (p[:, a1] <= bmax[a1]) & \
-                 (p[:, a2] >= bmin[a2]) & (p[:, a2] <= bmax[a2])        # :34-51 inclusive
+            ok = (p[:, a1] >= bmin[..., a1]) & (p[:, a1] <= bmax[..., a1]) & \
+                 (p[:, a2] >= bmin[..., a2]) & (p[:, a2] <= bmax[..., a2])        # :34-51 inclusive
             cand[:, col] = torch.where(ok, t, cand[:, col])
             col += 1
     top = cand.topk(k=2, dim=-1)[0]                                     # :60
@@ -214,6 +214,17 @@ def resolve_scene(bboxes: torch.Tensor, bkgd_bbox: torch.Tensor, frame_ids: Sequ
     return {"bmin": boxes[:, 0, :].clone(), "bmax": boxes[:, 6, :].clone(), "pivot": pivot}
 
 
+def box_table(bboxes: torch.Tensor, bkgd_bbox: torch.Tensor, scale: Optional[Sequence[float]], shift: Optional[Sequence]) -> torch.Tensor:
+    """(F, l, 2, 3) min / max corners of every layer's box at every frame after the scale / shift edits: what
+    `bboxes = self.bboxes.index_select(0, frame_id - 1)` (:193) followed by :207-242 gives a ray of frame `f` (row f-1)."""
+    Fn = bboxes.shape[0]
+    rows = []
+    for f in range(Fn):
+        sc = resolve_scene(bboxes, bkgd_bbox, [0.0] + [float(f + 1)] * bboxes.shape[1], scale, shift)
+        rows.append(torch.stack([sc["bmin"], sc["bmax"]], 1))
+    return torch.stack(rows, 0)
+
+
 def _inverse_edit(xyz, i, scale, shift, pivot, fine: bool):
     """modeling/layered_rfrender.py:293-303 (coarse) / :467-475 (fine, where a None shift entry also skips the scale)."""
     if shift is not None:
@@ -237,6 +248,8 @@ def render(nets: dict, scene: dict, rays: torch.Tensor, n1: int, n2: int,
     rays (N, 6+l) fp32; jitter (l,N,n1); u (l,N,n2).
     scene: bmin/bmax (l,3) (already edited, see ``resolve_scene``), pivot, scale, shift,
            shown (list of l bools), near, alpha, boarder.
+           Optional ``box_table`` (F,l,2,3) with ``shared_frame``: rays of a mixed-frame batch, each taking the boxes of ITS
+           frame id, `self.bboxes.index_select(0, frame_id - 1)` (:193; see ``box_table``).
     """
     rays = rays.to(F32)
     o, d = rays[:, :3], rays[:, 3:6]
@@ -284,8 +297,12 @@ def render(nets: dict, scene: dict, rays: torch.Tensor, n1: int, n2: int,
     # ---- coarse pass --------------------------------------------------------------
     ts, masks, rgbs, sigs = [], [], [], []
     xyzs = []
+    table = scene.get("box_table") if shared_frame else None
+    row = (rays[:, 6].to(torch.int64) - 1) if table is not None else None                            # :193
     for i in range(l):
-        t, xyz, m = stratified_samples(o, d, scene["bmin"][i], scene["bmax"][i], n1, jitter[i], i == 0)
+        bmin_i = scene["bmin"][i] if table is None else table[row, i, 0]
+        bmax_i = scene["bmax"][i] if table is None else table[row, i, 1]
+        t, xyz, m = stratified_samples(o, d, bmin_i, bmax_i, n1, jitter[i], i == 0)
         ts.append(t); masks.append(m)
         xyzs.append(_inverse_edit(xyz, i, scale, shift, pivot, fine=False))
     for i in range(l):

@@ -62,6 +62,8 @@ struct stnerf_ctx {
   size_t v_rays_bytes = 0, v_img_bytes[2] = {0, 0};
   cudaStream_t copy_in = nullptr, copy_out = nullptr;      // host<->device copies that overlap the kernels of other chunks
   std::vector<cudaEvent_t> ev_pool;                         // timing-disabled events, reused call after call
+  float* box_table = nullptr;  // [n_frames][l][2][3] per-frame boxes for rays with their own frame id (stnerf_set_box_table)
+  int box_frames = 0;
   bool no_fuse = false;        // STNERF_NO_FUSE=1 in the environment at create: keep the coarse compositing in its own kernel (A/B)
   int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
   RayIdMap idmap{0, 0, 0};     // stnerf_set_ray_ids
@@ -192,7 +194,7 @@ void stnerf_destroy(stnerf_handle c) {
     for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->space[f][i].blob); tc_free(c->space[f][i].tc); }
   for (int i = 0; i < STNERF_MAX_LAYERS; ++i) { cudaFree(c->motion[i].blob); tc_free(c->motion[i].tc); }
   cudaFree(c->h_rays); cudaFree(c->h_out); cudaFree(c->h_mask); cudaFree(c->any_frac);
-  cudaFree(c->v_rays); cudaFree(c->v_img[0]); cudaFree(c->v_img[1]);
+  cudaFree(c->v_rays); cudaFree(c->v_img[0]); cudaFree(c->v_img[1]); cudaFree(c->box_table);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
   if (c->copy_out) cudaStreamDestroy(c->copy_out);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -571,7 +573,7 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
     {
       ProfScope ps(c, 2, (double)n, -1, 1, st);
       rc = launch_sample(rch, n, ray_stride, c->dscene, l, n1, jitter ? jitter + c0 * n1 : nullptr, N * n1, seed, c0, c->idmap,
-                         c->t_coarse, R * c->cap_n1, mask, mask_ls, c->hit, R, c->counts, c->lerp_flags, st);
+                         c->t_coarse, R * c->cap_n1, mask, mask_ls, c->hit, R, c->counts, c->lerp_flags, st, c->box_table, c->box_frames);
       if (rc) return rc;
     }
     if (c->prof_on && c->prof_counts && c->prof_chunks < PROF_MAX_CHUNKS) {
@@ -835,6 +837,19 @@ int stnerf_debug_read_depths(stnerf_handle c, int what, int layer, float* dst, i
   const long long R = c->chunk_rays;
   const float* src = what ? c->t_fine + (size_t)layer * R * c->cap_s2 : c->t_coarse + (size_t)layer * R * c->cap_n1;
   STNERF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n_rays * S * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return STNERF_OK;
+}
+
+int stnerf_set_box_table(stnerf_handle c, const float* table_host, int n_frames) {
+  if (!c || n_frames < 0 || (n_frames > 0 && !table_host)) return STNERF_EINVAL;
+  STNERF_CUDA(cudaDeviceSynchronize());                  // a previous table may still be read by queued kernels
+  cudaFree(c->box_table);
+  c->box_table = nullptr; c->box_frames = 0;
+  if (n_frames == 0) return STNERF_OK;
+  const size_t bytes = (size_t)n_frames * c->l * 6 * sizeof(float);
+  if (cudaMalloc((void**)&c->box_table, bytes) != cudaSuccess) { cudaGetLastError(); return STNERF_ENOMEM; }
+  STNERF_CUDA(cudaMemcpy(c->box_table, table_host, bytes, cudaMemcpyHostToDevice));
+  c->box_frames = n_frames;
   return STNERF_OK;
 }
 

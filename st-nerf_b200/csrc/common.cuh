@@ -148,7 +148,8 @@ int launch_raygen(const float* Kinv, const float* T, int H, int W, int row0, int
 int launch_sample(const float* rays, long long n, int ray_stride, const DevScene& scene, int n_layers, int n1,
                   const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base, RayIdMap idmap,
                   float* t_coarse, long long t_layer_stride, uint8_t* mask, long long mask_layer_stride,
-                  int* hit, long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st);
+                  int* hit, long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st,
+                  const float* box_table = nullptr, int n_frames = 0);
 int launch_intersect_sample(const float* rays, long long n, int ray_stride, const float* bmin, const float* bmax,
                             int is_bkgd, int n1, const float* jitter, float* t, float* xyz, uint8_t* mask,
                             float* tfar_tnear, cudaStream_t st);

@@ -56,7 +56,7 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
               int n_layers, int n1, const float* __restrict__ jitter, long long jitter_layer_stride, uint64_t seed,
               long long ray_base, RayIdMap idmap, float* __restrict__ t_out, long long t_layer_stride, uint8_t* __restrict__ mask,
               long long mask_layer_stride, int* __restrict__ hit, long long hit_layer_stride, int* __restrict__ counts,
-              int* __restrict__ lerp_flags) {
+              int* __restrict__ lerp_flags, const float* __restrict__ box_table, int n_frames) {
   __shared__ float s_start[STNERF_MAX_LAYERS][SAMPLE_BLOCK];
   __shared__ float s_width[STNERF_MAX_LAYERS][SAMPLE_BLOCK];
   __shared__ int s_warp_hits[STNERF_MAX_LAYERS][SAMPLE_BLOCK / 32];
@@ -74,9 +74,20 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
     d[0] = p[3]; d[1] = p[4]; d[2] = p[5];
   }
   unsigned my_hits = 0;
+  // rays of a mixed-frame batch: the boxes of the ray's own frame, index_select(frame_id - 1) (layered_rfrender.py:193)
+  const float* my_boxes = nullptr;
+  if (box_table != nullptr && live) {
+    int f = (int)rays[r * ray_stride + 6] - 1;                    // .type(torch.int64): truncation
+    f = min(max(f, 0), n_frames - 1);
+    my_boxes = box_table + (size_t)f * n_layers * 6;
+  }
   for (int i = 0; i < n_layers; ++i) {
     float bmin[3] = {scene.bmin[i][0], scene.bmin[i][1], scene.bmin[i][2]};
     float bmax[3] = {scene.bmax[i][0], scene.bmax[i][1], scene.bmax[i][2]};
+    if (my_boxes != nullptr) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { bmin[a] = my_boxes[i * 6 + a]; bmax[a] = my_boxes[i * 6 + 3 + a]; }
+    }
     float start, width;
     bool h;
     ray_bins(o, d, bmin, bmax, i == 0, n1, start, width, h);
@@ -129,12 +140,14 @@ sample_kernel(const float* __restrict__ rays, long long n, int ray_stride, const
 int launch_sample(const float* rays, long long n, int ray_stride, const DevScene& scene, int n_layers, int n1,
                   const float* jitter, long long jitter_layer_stride, uint64_t seed, long long ray_base, RayIdMap idmap,
                   float* t_coarse, long long t_layer_stride, uint8_t* mask, long long mask_layer_stride, int* hit,
-                  long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st) {
+                  long long hit_layer_stride, int* counts, int* lerp_flags, cudaStream_t st, const float* box_table,
+                  int n_frames) {
   if (n <= 0) return STNERF_OK;
   const int grid = (int)((n + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK);
   sample_kernel<<<grid, SAMPLE_BLOCK, 0, st>>>(rays, n, ray_stride, scene, n_layers, n1, jitter,
                                                jitter_layer_stride, seed, ray_base, idmap, t_coarse, t_layer_stride, mask,
-                                               mask_layer_stride, hit, hit_layer_stride, counts, lerp_flags);
+                                               mask_layer_stride, hit, hit_layer_stride, counts, lerp_flags,
+                                               (scene.fid_shared && n_frames > 0) ? box_table : nullptr, n_frames);
   STNERF_LAUNCH_CHECK();
   return STNERF_OK;
 }

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "stnerf_weights_export": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "stnerf_weights_import": (C.c_int, [_P, _P, C.c_size_t]),
     "stnerf_set_scene": (C.c_int, [_P, C.POINTER(Scene)]),
+    "stnerf_set_box_table": (C.c_int, [_P, _P, C.c_int]),
     "stnerf_render": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "stnerf_render_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
     "stnerf_reserve_host": (C.c_int, [_P, C.c_int64, C.c_int]),

@@ -165,21 +165,10 @@ class LayeredRFRender(torch.nn.Module):
         end = self.bboxes[math.ceil(float_frame_id), layer_id]
         return torch.lerp(start, end, float_frame_id - math.floor(float_frame_id))
 
-    def _resolve_scene(self, frame_ids_row0, density_threshold, bkgd_density_threshold) -> L.Scene:
+    def _edit_boxes(self, boxes, table, bk):
+        """Scale / shift edits of one set of boxes (l,8,3) about the pivot of the FIRST table row (layered_rfrender.py:216-242).
+        Returns the min corners (l,3), max corners (l,3) and the pivot."""
         l = self.layer_num + 1
-        if self.bboxes is None or self.bkgd_bbox is None:
-            raise RuntimeError("set_bboxes / set_bkgd_bbox must be called before rendering")
-        table = self.bboxes.detach().to("cpu", torch.float32)
-        bk = self.bkgd_bbox.detach().to("cpu", torch.float32).reshape(1, 8, 3)
-        self.bboxes = table                                               # what .cuda() would have kept on the model
-        boxes = [bk[0].clone()]
-        for i in range(self.layer_num):
-            if self.retiming:
-                f = torch.tensor(float(frame_ids_row0[i + 1]), dtype=torch.float32) - 1       # (:200)
-                boxes.append(self.bbox_interpolation(f, i))
-            else:                                                         # index_select(int64(frame_id) - 1) (:193)
-                boxes.append(table[int(float(frame_ids_row0[i + 1])) - 1, i])
-        boxes = torch.stack(boxes, 0)                                     # (l,8,3)
         first = torch.cat([bk, table[0]], 0)                              # (:216-220)
         centre = first.mean(1)
         centre[:, 2] = first[:, 1, 2]                                     # (:226)
@@ -203,6 +192,35 @@ class LayeredRFRender(torch.nn.Module):
                            torch.stack([hi[:, 0], hi[:, 1], hi[:, 2]], -1), torch.stack([lo[:, 0], hi[:, 1], hi[:, 2]], -1)], 1)
         if not torch.equal(ref, boxes):
             raise ValueError("bounding boxes must be axis-aligned with the corner order of data/datasets/frame_dataset.py:187-188")
+        return lo, hi, pivot
+
+    def _box_table(self) -> torch.Tensor:
+        """(F, l, 2, 3): min / max corners of every layer at every frame after the edits -- what a ray of frame f gets from
+        `self.bboxes.index_select(0, frame_id - 1)` (layered_rfrender.py:193) followed by :207-242 (row f-1)."""
+        table = self.bboxes.detach().to("cpu", torch.float32)
+        bk = self.bkgd_bbox.detach().to("cpu", torch.float32).reshape(1, 8, 3)
+        rows = []
+        for f in range(table.shape[0]):
+            lo, hi, _ = self._edit_boxes(torch.cat([bk, table[f]], 0).clone(), table, bk)
+            rows.append(torch.stack([lo, hi], 1))
+        return torch.stack(rows, 0)
+
+    def _resolve_scene(self, frame_ids_row0, density_threshold, bkgd_density_threshold) -> L.Scene:
+        l = self.layer_num + 1
+        if self.bboxes is None or self.bkgd_bbox is None:
+            raise RuntimeError("set_bboxes / set_bkgd_bbox must be called before rendering")
+        table = self.bboxes.detach().to("cpu", torch.float32)
+        bk = self.bkgd_bbox.detach().to("cpu", torch.float32).reshape(1, 8, 3)
+        self.bboxes = table                                               # what .cuda() would have kept on the model
+        boxes = [bk[0].clone()]
+        for i in range(self.layer_num):
+            if self.retiming:
+                f = torch.tensor(float(frame_ids_row0[i + 1]), dtype=torch.float32) - 1       # (:200)
+                boxes.append(self.bbox_interpolation(f, i))
+            else:                                                         # index_select(int64(frame_id) - 1) (:193)
+                boxes.append(table[int(float(frame_ids_row0[i + 1])) - 1, i])
+        boxes = torch.stack(boxes, 0)                                     # (l,8,3)
+        lo, hi, pivot = self._edit_boxes(boxes, table, bk)
         sc = L.Scene()
         for i in range(l):
             for a in range(3):
@@ -259,9 +277,7 @@ class LayeredRFRender(torch.nn.Module):
             # evaluator rays [o,d,frame_id] (engine/layered_trainer.py:36,383): boxes by frame id (:193), no thresholds.
             # One image per call shares its frame id; mixed-frame training batches are outside the render hot path.
             self.retiming = False                                        # (:157-158)
-            if not bool((rays[:, 6] == rays[0, 6]).all()):
-                raise NotImplementedError("7-column rays with per-ray frame ids (training batches, per-ray bbox lookup "
-                                          "layered_rfrender.py:193) are outside the render hot path")
+            per_ray_frames = not bool((rays[:, 6] == rays[0, 6]).all())  # a mixed-frame batch: boxes per ray (:193)
         else:
             raise ValueError("undefined ray format in LayeredRFRender, ray dimension is %d" % width)   # (:162-163)
         if not rays.is_cuda:
@@ -274,6 +290,17 @@ class LayeredRFRender(torch.nn.Module):
         if not self.retiming:
             frame_ids = frame_ids[:1].expand(l)                          # index_select(frame_id - 1) for every layer (:193)
         nat.set_scene(self._resolve_scene(frame_ids, density_threshold, bkgd_density_threshold))
+        if width == 7 and per_ray_frames:
+            ids = rays[:, 6]
+            if float(ids.min()) < 1 or float(ids.max()) >= self.bboxes.shape[0] + 1:
+                raise IndexError("frame id out of range for index_select(0, frame_id - 1) (layered_rfrender.py:193)")
+            key = (id(self.bboxes), repr(self.scale), repr(self.shift))
+            if getattr(self, "_table_key", None) != key:
+                nat.set_box_table(self._box_table())
+                self._table_key = key
+        elif getattr(self, "_table_key", None) is not None:
+            nat.set_box_table(None)
+            self._table_key = None
         jitter, u = self._inject if self._inject is not None else (None, None)
         self._inject = None
         self.seed += 1

@@ -95,6 +95,16 @@ class NativeRenderer:
         self._scene = scene
         L.check(L.lib().stnerf_set_scene(self._h, C.byref(scene)), "stnerf_set_scene")
 
+    def set_box_table(self, table: Optional[torch.Tensor]):
+        """table (F, l, 2, 3) host fp32: edited min/max corners per frame and layer, for rays that carry their own frame id
+        (stnerf_set_box_table); None removes it."""
+        if table is None:
+            L.check(L.lib().stnerf_set_box_table(self._h, None, 0), "stnerf_set_box_table")
+            return
+        t = table.detach().to("cpu", torch.float32).contiguous()
+        assert t.dim() == 4 and tuple(t.shape[1:]) == (self.l, 2, 3), tuple(t.shape)
+        L.check(L.lib().stnerf_set_box_table(self._h, L.ptr(t), int(t.shape[0])), "stnerf_set_box_table")
+
     # ---- render ----------------------------------------------------------------------------------------
     def render(self, rays: torch.Tensor, n1: int, n2: int, only_coarse: bool = False,
                jitter: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, seed: int = 0,

@@ -42,6 +42,11 @@ CASES = {
     # evaluator layout: 7-column rays [o,d,frame_id], boxes by index_select, no thresholds (engine/layered_trainer.py:36,383)
     "tkd_eval_7col": dict(weights="taekwondo", L=2, space_time=True, n1=64, n2=128, seven=True,
                           frame_ids=[10, 10, 10], thr=(20.0, 0.8), n_rays=128, ray_seed=8),
+    # a mixed-frame batch as the trainer draws it: 7-column rays, every ray with its OWN integer frame id -> boxes per ray by
+    # index_select(frame_id - 1) (modeling/layered_rfrender.py:193), shift/scale edits on top
+    "tkd_train_7col_mixed": dict(weights="taekwondo", L=2, space_time=True, n1=64, n2=128, seven=True, mixed_frames=(3, 60),
+                                 frame_ids=[10, 10, 10], thr=(20.0, 0.8), n_rays=160, ray_seed=9,
+                                 shift=[[0, 0, 0], [0, 0.5, 0], [0, -0.5, 0]], scale=[1, 0.9, 1.2]),
     # BASELINE config #3 flavour: walking nets replicated round-robin to 4 performer layers
     "walk_L4_64_128": dict(weights="walking", L=4, space_time=False, n1=64, n2=128,
                            frame_ids=[0, 30, 31, 32, 33], thr=(20.0, 0.8), near=4.0, n_rays=128, ray_seed=6),
@@ -97,6 +102,9 @@ def rays_for(case: dict) -> torch.Tensor:
     rays = torch.cat([grid, torch.stack(aimed, 0)], 0)
     ids = case["frame_ids"][:1] if case.get("seven") else case["frame_ids"]
     fid = torch.tensor(ids, dtype=torch.float32)[None].expand(n, -1)
+    if case.get("mixed_frames"):                      # one integer frame id per ray
+        lo_f, hi_f = case["mixed_frames"]
+        fid = torch.from_numpy(rs.randint(lo_f, hi_f + 1, size=(n, 1)).astype(np.float32))
     return torch.cat([rays, fid], 1).contiguous()
 
 
@@ -119,6 +127,8 @@ def scene_for(case: dict):
     sc.update(scale=case.get("scale"), shift=case.get("shift"),
               shown=[i not in case.get("hidden", []) for i in range(l)],
               near=case.get("near", 0.0), alpha=case.get("alpha", 1.0), boarder=1e10)
+    if case.get("mixed_frames"):
+        sc["box_table"] = O.box_table(frames, bkgd, case.get("scale"), case.get("shift"))
     return sc
 
 
