@@ -49,6 +49,10 @@ struct stnerf_ctx {
   long long last_chunk_rays = 0;       // geometry of the most recent chunk (stnerf_debug_read_depths)
   int last_n1 = 0, last_s2 = 0;
   float *t_coarse = nullptr, *raw_coarse = nullptr, *t_fine = nullptr, *raw_fine = nullptr, *xyz = nullptr;
+  // flow reuse (fine pass): per performer layer the coarse pass' deformed points, the new depths and the origin map of t_fine
+  float *xyz_coarse = nullptr, *z_new = nullptr;
+  uint8_t* src_map = nullptr;
+  bool no_reuse = false;       // STNERF_NO_REUSE=1 at create: the fine pass evaluates the MotionNet on all n1+n2 depths (A/B)
   float* cbuf = nullptr;       // per-slot rgb_net.1 bias of the SpaceNet being evaluated (tensor-core modes)
   uint8_t* mask_ws = nullptr;
   int *hit = nullptr, *counts = nullptr, *lerp_flags = nullptr;
@@ -93,6 +97,8 @@ struct ProfScope {
 
 static void free_ws(stnerf_ctx* c) {
   cudaFree(c->t_coarse); cudaFree(c->raw_coarse); cudaFree(c->t_fine); cudaFree(c->raw_fine); cudaFree(c->xyz);
+  cudaFree(c->xyz_coarse); cudaFree(c->z_new); cudaFree(c->src_map);
+  c->xyz_coarse = c->z_new = nullptr; c->src_map = nullptr;
   cudaFree(c->cbuf); c->cbuf = nullptr;
   cudaFree(c->mask_ws); cudaFree(c->hit); cudaFree(c->counts); cudaFree(c->lerp_flags);
   c->t_coarse = c->raw_coarse = c->t_fine = c->raw_fine = c->xyz = nullptr;
@@ -117,6 +123,9 @@ static int ensure_ws(stnerf_ctx* c, int n1, int s2) {
   rc |= A((void**)&c->t_fine, l * R * cs2 * 4);
   rc |= A((void**)&c->raw_fine, l * R * cs2 * 16);
   rc |= A((void**)&c->xyz, R * cs2 * 12);
+  rc |= A((void**)&c->xyz_coarse, l * R * cn1 * 12);
+  rc |= A((void**)&c->z_new, l * R * cs2 * 4);
+  rc |= A((void**)&c->src_map, l * R * cs2);
   rc |= A((void**)&c->cbuf, R * 128 * 4);
   rc |= A((void**)&c->mask_ws, l * R);
   rc |= A((void**)&c->hit, l * R * 4);
@@ -181,6 +190,7 @@ int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   c->precision = d->precision;
   c->chunk_rays = d->chunk_rays > 0 ? d->chunk_rays : 65536;
   if (const char* e = getenv("STNERF_NO_FUSE")) c->no_fuse = (e[0] == '1');
+  if (const char* e = getenv("STNERF_NO_REUSE")) c->no_reuse = (e[0] == '1');
   if (cudaMalloc((void**)&c->any_frac, 4) != cudaSuccess) { delete c; return STNERF_ENOMEM; }
   *out = c;
   return STNERF_OK;
@@ -478,9 +488,11 @@ static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, 
 
 // `fuse` (coarse pass only): template of the per-layer fusion request (everything but the layer-specific fields), or null.
 // `want_raw`: the (rgb, sigma) samples must reach HBM (a later kernel composites them); false only with `fuse`.
+// `reuse_n1` > 0 (fine pass): the MotionNet runs on the S - reuse_n1 NEW depths only; the flow of the coarse depths is the coarse
+// pass' (xyz_coarse), stitched together through the origin map the merge wrote (z_new / src_map).
 static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_stride, bool fine, int S, cudaStream_t st,
                     int chunk_slot, const FuseCoarse* fuse = nullptr, bool want_raw = true, float* coarse_imgs = nullptr,
-                    long long plane = 0) {
+                    long long plane = 0, int reuse_n1 = 0) {
   const long long R = c->chunk_rays;
   const float* tbuf = fine ? c->t_fine : c->t_coarse;
   float* rawbuf = fine ? c->raw_fine : c->raw_coarse;
@@ -502,6 +514,8 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
       f = *fuse;
       f.on = 1; f.layer = i; f.is_bkgd = (i == 0);
       f.t_fine = c->t_fine + (size_t)i * R * c->cap_s2;
+      f.z_new = fuse->z_new ? c->z_new + (size_t)i * R * c->cap_s2 : nullptr;
+      f.src_map = fuse->z_new ? c->src_map + (size_t)i * R * c->cap_s2 : nullptr;
       f.u = fuse->u ? fuse->u + (size_t)i * fuse->n_total * fuse->n2 : nullptr;     // [layer][ray of the call][n2], chunk offset applied by the caller
       f.img = coarse_imgs ? coarse_imgs + (size_t)(1 + i) * plane : nullptr;
     }
@@ -515,10 +529,29 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     s.hit = c->hit + (size_t)i * R;
     s.count = c->counts + i;
     s.n_slots_cap = n;
-    rc = run_motionnet(c, s, c->motion[i], c->lerp_flags + i, -1, c->xyz, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
+    // the coarse pass keeps every performer's deformed points (the fine pass may reuse them); the fine pass has one scratch
+    float* xyz_out = fine ? c->xyz : c->xyz_coarse + (size_t)i * R * c->cap_n1 * 3;
+    // reuse needs the same inverse edit in both passes (a None shift entry skips the fine-pass scale only, layered_rfrender.py:468-469)
+    const bool reuse = fine && reuse_n1 > 0 && c->scene.scale_fine_on[i] == c->scene.scale_coarse_on[i];
+    if (reuse) {
+      PointSrc m = s;                                            // MotionNet on the n2 new depths of every hit ray
+      m.t = c->z_new + (size_t)i * R * c->cap_s2;
+      m.S = S - reuse_n1;
+      rc = run_motionnet(c, m, c->motion[i], c->lerp_flags + i, -1, xyz_out, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
+      if (rc) return rc;
+      s.mode = SRC_XYZ_MAP;
+      s.pos = c->xyz_coarse + (size_t)i * R * c->cap_n1 * 3;
+      s.pos2 = xyz_out;
+      s.src_map = c->src_map + (size_t)i * R * c->cap_s2;
+      s.n_first = reuse_n1;
+      rc = run_spacenet(c, s, c->space[1][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1, nullptr);
+      if (rc) return rc;
+      continue;
+    }
+    rc = run_motionnet(c, s, c->motion[i], c->lerp_flags + i, -1, xyz_out, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1);
     if (rc) return rc;
     s.mode = SRC_XYZ;
-    s.pos = c->xyz;
+    s.pos = xyz_out;
     rc = run_spacenet(c, s, c->space[fine ? 1 : 0][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1,
                       fuse ? &f : nullptr);
     if (rc) return rc;
@@ -592,9 +625,13 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
       if (i == 0 || c->scene.shown[i]) fused_layers |= fuse ? (1u << i) : 0u;
       else hidden_any = true;
     }
+    // Flow reuse: the merge (fused or stand-alone register path) also writes the new depths and the origin of every fine depth, so
+    // the fine pass runs the MotionNet on the n2 new depths only (same network, same points for the other n1: SURVEY A.6).
+    const bool reuse = n2 > 0 && c->precision != STNERF_PREC_FP32_SIMT && n1 <= 128 && n2 <= 256 && S2 <= 256 && !c->no_reuse;
     FuseCoarse ft;
     memset(&ft, 0, sizeof(ft));
     if (fuse) {
+      ft.z_new = reuse ? c->z_new : nullptr;
       ft.n1 = n1; ft.n2 = n2; ft.u = u ? u + c0 * n2 : nullptr; ft.seed = seed; ft.idmap = c->idmap; ft.ray_base = c0;
       ft.n_total = N; ft.pixels = out.pixels; ft.near_plane = c->dscene.near_plane; ft.thr = c->dscene.thr_layer;
       ft.boarder = c->dscene.boarder; ft.apply_thr = c->dscene.apply_thr;
@@ -610,6 +647,7 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
     a.mask = mask; a.mask_layer_stride = mask_ls;
     a.u = u ? u + c0 * n2 : nullptr; a.u_layer_stride = N * n2;
     a.t_fine = c->t_fine; a.tf_layer_stride = R * c->cap_s2;
+    if (reuse) { a.z_new = c->z_new; a.zn_layer_stride = R * c->cap_s2; a.src_map = c->src_map; a.sm_layer_stride = R * c->cap_s2; }
     a.out = out.coarse; a.pixel_layout = out.pixels; a.n_total = N; a.ray_base = c0; a.n = n;
     a.S = n1; a.n2 = n2; a.fine = 0; a.seed = seed; a.idmap = c->idmap;
     if (!fuse || out.coarse != nullptr || hidden_any) {
@@ -618,7 +656,7 @@ static int render_core(stnerf_ctx* c, const float* rays, long long n_rays, int r
       if (rc) return rc;
     }
     if (n2 > 0) {
-      rc = run_nets(c, rch, n, ray_stride, true, S2, st, chunk_slot);
+      rc = run_nets(c, rch, n, ray_stride, true, S2, st, chunk_slot, nullptr, true, nullptr, 0, reuse ? n1 : 0);
       if (rc) return rc;
       a.t = c->t_fine; a.t_layer_stride = R * c->cap_s2;
       a.raw = c->raw_fine; a.raw_layer_stride = R * c->cap_s2 * 4;

@@ -64,7 +64,7 @@ struct MotionNetW {
 };
 
 // Where a tile of points comes from.
-enum { SRC_EXPLICIT = 0, SRC_MARCH = 1, SRC_XYZ = 2 };
+enum { SRC_EXPLICIT = 0, SRC_MARCH = 1, SRC_XYZ = 2, SRC_XYZ_MAP = 3 };
 struct PointSrc {
   int mode;
   // SRC_EXPLICIT: per-point arrays (unit entry points)
@@ -75,6 +75,11 @@ struct PointSrc {
   // SRC_MARCH / SRC_XYZ: points = (slot, k), ray = hit ? hit[slot] : slot
   const float* rays;         // (n, ray_stride): o, d, frame ids
   int ray_stride;
+  // SRC_XYZ_MAP (fine pass with flow reuse): position k of a slot's S depths came from coarse sample m = src_map[ray*S + k] < n_first
+  // (deformed position pos[(slot*n_first + m)*3]) or from new depth m - n_first (pos2[(slot*(S - n_first) + m - n_first)*3])
+  const uint8_t* src_map;
+  const float* pos2;
+  int n_first;
   const int* hit;            // slot -> ray, or null (identity: background)
   const int* count;          // device-side number of slots, or null
   long long n_slots;         // slots when count == null; P for SRC_EXPLICIT (with S == 1)
@@ -167,6 +172,10 @@ struct CompositeArgs {
   long long u_layer_stride;
   float* t_fine;           // out (coarse pass with n2 > 0): [layer][ray][n1+n2]
   long long tf_layer_stride;
+  float* z_new;            // out, optional: [layer][ray][n2] the new depths, ascending (flow reuse, see resample.cuh)
+  long long zn_layer_stride;
+  uint8_t* src_map;        // out, optional: [layer][ray][n1+n2] origin of every fine depth
+  long long sm_layer_stride;
   float* out;              // images of this pass: [img][5*n_total], or null (coarse pass: resampling only, no images)
   unsigned skip_layers;    // bit i: layer i's own image + resampling were produced elsewhere (fused SpaceNet kernel): gather only
   int pixel_layout;        // 0: plane = rgb (N,3) | depth (N) | acc (N);  1: plane = (N,5) pixel-interleaved

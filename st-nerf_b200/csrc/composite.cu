@@ -207,7 +207,7 @@ static_assert(STNERF_MAX_S <= (1 << ORDER_K_BITS) && STNERF_MAX_LAYERS <= (1 << 
 // NT, NZ > 0: the coarse pass' per-layer composite + resampling runs register-resident (resample.cuh: NT = ceil(n1/32) depth slots
 // and NZ = pow2 >= ceil(n2/32) new-depth slots per lane); NT == 0: generic shared-memory path (fine pass, unusual sample counts).
 template <int NT, int NZ>
-__global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scene, int n_layers, const PassSmem L) {
+__global__ void __launch_bounds__(256, 3) composite_pass_kernel(const CompositeArgs a, const DevScene scene, int n_layers, const PassSmem L) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* base = smem + (size_t)warp * L.per_warp_floats;
@@ -301,7 +301,9 @@ __global__ void composite_pass_kernel(const CompositeArgs a, const DevScene scen
               return make_float3(sigmoidf_ref(v.x), sigmoidf_ref(v.y), sigmoidf_ref(v.z));
             },
             [up, seed, i, gid](int j) { return up ? up[j] : philox_uniform(seed, 64u + (uint32_t)i, gid, (uint32_t)j); },
-            s_cdf, want_w ? a.t_fine + i * a.tf_layer_stride + r * (S + n2) : nullptr, lane, lo);
+            s_cdf, want_w ? a.t_fine + i * a.tf_layer_stride + r * (S + n2) : nullptr, lane, lo,
+            (want_w && a.z_new) ? a.z_new + i * a.zn_layer_stride + r * n2 : nullptr,
+            (want_w && a.z_new) ? a.src_map + i * a.sm_layer_stride + r * (S + n2) : nullptr);
         write_pixel(oimg, rg, a.n_total, pixels, lo.pix, lane);
         if (i == 0) {
 #pragma unroll
@@ -436,6 +438,9 @@ static int launch_pass_t(const CompositeArgs& a, const DevScene& scene, int n_la
   const size_t smem = per_warp * wpb;
   auto kern = composite_pass_kernel<NT, NZ>;
   STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // three blocks of 8 warps per SM (85 registers per thread): ask for the largest shared-memory carve-out so that shared memory
+  // does not cap the residency below that
+  STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm * wpb > 64) per_sm = 64 / wpb;
   if (per_sm < 1) per_sm = 1;

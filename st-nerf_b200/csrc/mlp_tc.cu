@@ -329,6 +329,12 @@ __device__ __forceinline__ Pt fetch_pt(const PointSrc& s, long long p, long long
     q.x = s.pos[3 * p]; q.y = s.pos[3 * p + 1]; q.z = s.pos[3 * p + 2];
     return q;
   }
+  if (s.mode == SRC_XYZ_MAP) {           // fine pass with flow reuse: where did depth k of this ray come from?
+    const int m = s.src_map[ray * s.S + k];
+    const float* pp = (m < s.n_first) ? s.pos + 3 * (slot * s.n_first + m) : s.pos2 + 3 * (slot * (s.S - s.n_first) + (m - s.n_first));
+    q.x = pp[0]; q.y = pp[1]; q.z = pp[2];
+    return q;
+  }
   const float tt = s.t[ray * s.S + k];
   float v[3] = {__fadd_rn(__fmul_rn(tt, rp[3]), rp[0]), __fadd_rn(__fmul_rn(tt, rp[4]), rp[1]),
                 __fadd_rn(__fmul_rn(tt, rp[5]), rp[2])};
@@ -586,7 +592,8 @@ __device__ __noinline__ void fused_composite_loop(const TcParams& P, const float
                                __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v.z))));
           },
           [up, seed, stream, gid](int jj) { return up ? up[jj] : philox_uniform(seed, stream, gid, (uint32_t)jj); },
-          cdf, F.t_fine + ray * (n1 + n2), lane, lo);
+          cdf, F.t_fine + ray * (n1 + n2), lane, lo, F.z_new ? F.z_new + ray * n2 : nullptr,
+          F.z_new ? F.src_map + ray * (n1 + n2) : nullptr);
       if (F.img && lane < 5) {
         const long long rg = F.ray_base + ray;
         const float v = lane == 0 ? lo.pix[0] : lane == 1 ? lo.pix[1] : lane == 2 ? lo.pix[2] : lane == 3 ? lo.pix[3] : lo.pix[4];

@@ -17,6 +17,8 @@ struct FuseCoarse {
   RayIdMap idmap;
   long long ray_base;          // first ray of the chunk within the call (Philox key, image row)
   float* t_fine;               // out: this layer's [ray][n1 + n2] sorted depths
+  float* z_new;                // out, optional (with src_map): this layer's [ray][n2] new depths, ascending
+  uint8_t* src_map;            // out, optional: this layer's [ray][n1 + n2] origin of every fine depth (resample.cuh)
   float* img;                  // out: this layer's coarse image (one pixel per hit ray), or null
   long long n_total;           // rays of the whole call (plane geometry of img)
   int pixels;                  // img layout: 0 planes, 1 pixel-interleaved

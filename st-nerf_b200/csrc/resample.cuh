@@ -95,10 +95,14 @@ struct LayerOut {
 // rgb_at(s): sigmoid colour of that sample -- only called where the weight is non-zero.
 // get_u(j): uniform j of this (ray, layer).   cdf: >= n1 floats of shared memory owned by this warp.
 // tf: global, n1+n2 floats: receives sort(cat(t, z)) (nullptr: no resampling, image only).
+// zs / src (optional, both or neither; n1+n2 <= 256): the n2 new depths in ascending order, and for every position of `tf`
+// where its depth came from -- k < n1: coarse sample k, n1 + e: new depth e.  Lets the fine pass evaluate the MotionNet on the
+// new depths only and take the flow of the coarse depths from the coarse pass (same network, same points).
 template <int NT, int NZ, typename RgbAt, typename GetU>
 __device__ __forceinline__ void composite_resample_ray(const float (&t)[NT], const float (&sg)[NT], int n1, int n2, float boarder,
                                                        RgbAt rgb_at, GetU get_u, float* cdf, float* __restrict__ tf, int lane,
-                                                       LayerOut& out) {
+                                                       LayerOut& out, float* __restrict__ zs = nullptr,
+                                                       uint8_t* __restrict__ src = nullptr) {
   // ---- gen_weight + VolumeRenderer.forward (render_layer.py:8-58) -----------------------------------------------------
   float w[NT];
   float carry = 1.0f;
@@ -222,6 +226,7 @@ __device__ __forceinline__ void composite_resample_ray(const float (&t)[NT], con
         }
         const int pos = e + lo;
         tf[pos] = key;
+        if (zs != nullptr) { zs[e] = key; src[pos] = (uint8_t)(n1 + e); }
 #pragma unroll
         for (int wd = 0; wd < NW; ++wd)
           if ((pos >> 5) == wd) occ[wd] |= 1u << (pos & 31);
@@ -248,6 +253,7 @@ __device__ __forceinline__ void composite_resample_ray(const float (&t)[NT], con
           }
         }
         tf[pos] = t[s];
+        if (src != nullptr) src[pos] = (uint8_t)(s * 32 + lane);
       }
     }
   } else {
@@ -266,6 +272,14 @@ __device__ __forceinline__ void composite_resample_ray(const float (&t)[NT], con
 #pragma unroll
     for (int s = 0; s < NR; ++s)
       if (s * 32 + lane < S2) tf[s * 32 + lane] = v[s];
+    // no source map for such a ray (it cannot arise for a performer box: its depths ascend unless a coordinate is NaN); keep the
+    // consumers inside their buffers
+    if (zs != nullptr) {
+#pragma unroll
+      for (int q = 0; q < NZ; ++q)
+        if (q * 32 + lane < n2) zs[q * 32 + lane] = z[q];
+      for (int k = lane; k < S2; k += 32) src[k] = (uint8_t)min(k, n1 + n2 - 1);
+    }
   }
   __syncwarp();
 }

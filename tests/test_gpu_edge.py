@@ -155,3 +155,32 @@ def test_coarse_fusion_is_not_observable(monkeypatch):
         for a, b in zip(outs[True], outs[False]):
             for k in a:
                 assert np.array_equal(a[k], b[k]), (name, k, float(np.abs(a[k].astype(np.float64) - b[k]).max()))
+
+
+def test_flow_reuse_is_not_observable(monkeypatch):
+    """The fine pass takes the MotionNet flow of the n1 coarse depths from the coarse pass (same network, same points)
+    and evaluates the MotionNet on the n2 new depths only; the origin map comes from the merge (csrc/resample.cuh).  Every output
+    is bit-identical with the reuse switched off (STNERF_NO_REUSE=1): integer and fractional frame ids (MotionNet lerp), shift /
+    scale edits, a `None` shift entry (which disables the fine-pass scale of that layer only -> no reuse there), 64+192 samples,
+    fused and stand-alone merge."""
+    variants = [("tkd_64_128", {}), ("tkd_edit_frac", {}), ("tkd_edit_frac", {"shift": [[0, 0, 0], None, [0, -2, 0]]}),
+                ("walk_L4_64_128", {"n2": 192}), ("walk_90_30_hide", {})]
+    for name, over in variants:
+        case = dict(C.CASES[name], **over)
+        if C.state_dict_for(case) is None:
+            pytest.skip("checkpoint copy absent")
+        rays = C.rays_for(case).cuda()
+        outs = {}
+        for reuse in (True, False):
+            if reuse:
+                monkeypatch.delenv("STNERF_NO_REUSE", raising=False)
+            else:
+                monkeypatch.setenv("STNERF_NO_REUSE", "1")
+            model = build_case_model(case, "exact")
+            model.seed = 17
+            with torch.no_grad():
+                o = model(rays, None, None, density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+            outs[reuse] = C.flatten_outputs(*o)
+            del model
+        for k in outs[True]:
+            assert np.array_equal(outs[True][k], outs[False][k]), (name, over, k, float(np.abs(outs[True][k].astype(np.float64) - outs[False][k]).max()))
