@@ -67,7 +67,8 @@ class ShardedViewRenderer:
         self.rp = padded_rows(height, world)          # every rank renders rows_pad rows (rows past H-1 are discarded)
         self.l = native.l
         self._gather = {}                             # batch size -> persistent (world, B, l+1, rp*W, 5) buffer
-        self.collective_ms: Optional[float] = None    # device time of the last all-gather (CUDA events), when timed
+        self._coarse = {}                             # batch size -> scratch for the coarse images (with_coarse=True)
+        self._timing = None                           # CUDA events around the last timed all-gather
 
     def gather_buffer(self, batch: int) -> torch.Tensor:
         buf = self._gather.get(batch)
@@ -83,9 +84,8 @@ class ShardedViewRenderer:
         buf = self.gather_buffer(len(views))
         coarse = None
         if with_coarse:
-            coarse = self._coarse.get(len(views)) if hasattr(self, "_coarse") else None
+            coarse = self._coarse.get(len(views))
             if coarse is None:
-                self._coarse = getattr(self, "_coarse", {})
                 coarse = self._coarse[len(views)] = torch.empty_like(buf[self.rank])
         self.nat.render_views(views, self.H, self.W, self.n1, self.n2, row0=self.rank, row_step=self.world, n_rows=self.rp,
                               out=buf[self.rank], coarse_out=coarse)
@@ -105,7 +105,7 @@ class ShardedViewRenderer:
         return rows_view(buf, self.W)
 
     def last_collective_ms(self) -> Optional[float]:
-        t = getattr(self, "_timing", None)
+        t = self._timing
         if t is None:
             return None
         t[1].synchronize()
