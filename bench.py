@@ -289,7 +289,7 @@ def measure(wl, precision, steps, warmup, rank, world, local_rank, want_e2e=True
 
     # ---- e2e: host buffers through the C-ABI (H2D rays + D2H every plane inside the timed region), same step count ------
     if want_e2e:
-        n_views_host = min(VIEWS, max(1, steps), 4)
+        n_views_host = min(VIEWS, max(1, steps))           # the SAME views as the timed steps of `value` (work depends on the view)
         rays_host = []
         for v in range(n_views_host):
             K, T = cams[(warmup + v) % VIEWS]

@@ -23,8 +23,9 @@
 // every 64-column chunk and the half of the encoding frequencies the thread computes for its row.  (MotionNet, 320 threads:
 // the same roles without the two spare warps, epilogue warps 2..9.)
 //
-// Build flags: SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not
-// faster: DESIGN.md 8.1); MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout (A/B reference).
+// Build flags: SPACE_WSHARE=0 switches the shared weight stream off (every CTA then pulls all 1.8 MB per tile from L2 itself);
+// SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not faster: DESIGN.md 8);
+// MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout (A/B reference).
 //
 // Restates modeling/spacenet.py:101-160, modeling/motion_net.py:34-71, utils/dimension_kernel.py:24-33.
 #include <cuda_fp16.h>
@@ -39,6 +40,10 @@ namespace {
 #ifndef SPACE_CTA_PAIR
 #define SPACE_CTA_PAIR 0              // 1: SpaceNet tiles run as CTA pairs sharing one cta_group::2 accumulator (see mlp_tc_kernel)
 #endif
+#ifndef SPACE_WSHARE
+#define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
+#endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
+                                      //    0: every CTA streams all weights itself (A/B reference)
 #ifndef MOTION_CTAS_PER_SM
 #define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
@@ -99,6 +104,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// Multicast forms for the shared weight stream (SPACE_WSHARE): the copy lands at the same shared-memory offset of every CTA in
+// `mask` and completes bytes on the mbarrier at the same offset there; the commit arrives on that barrier in every CTA of `mask`.
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -551,13 +568,14 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 // warp `j` composites slot 2*tile+j from the rows the epilogue warps left in `rows` (float4 per row: rgb logits, sigma).
 template <int NZ>
 __device__ __noinline__ void fused_composite_loop(const TcParams& P, const float* rows, float* cdf, uint32_t bar_full, uint32_t bar_empty,
-                                                  long long n_tiles, int j, int lane) {
+                                                  long long n_tiles, int j, int lane, bool clustered) {
   const FuseCoarse& F = P.fuse;
   const PointSrc& src = P.src;
   const long long n_slots = src.count ? (long long)(*src.count) : src.n_slots;
   const int n1 = 64, n2 = F.n2;
   uint32_t n = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+  // (clustered: the CTAs of a cluster run the same number of tiles, the odd one out a tile past the end -- all slots invalid)
+  for (long long tile = blockIdx.x; clustered ? ((tile & ~1LL) < n_tiles) : (tile < n_tiles); tile += gridDim.x, ++n) {
     mbar_wait(bar_full, n & 1);
     const long long slot = tile * 2 + j;
     if (slot < n_slots) {
@@ -615,11 +633,15 @@ __device__ __noinline__ void fused_composite_loop(const TcParams& P, const float
 // output columns); the leader (cluster rank 0) issues the MMAs for both, so per SM the B operand reads and the L2 -> shared
 // weight traffic are halved.  Barriers the leader's MMA warp waits on collect arrivals from both CTAs (remote arrives);
 // `tcgen05.commit` multicasts to the same barrier in both CTAs.
-template <int NET, bool PAIR = false>
+// WSHARE: the two CTAs of a cluster keep their own tiles, accumulators and MMAs (cta_group::1) but share the WEIGHT STREAM: CTA r
+// pulls rows [r*N/2, (r+1)*N/2) of every stage from L2 and multicasts them into both shared memories, so the L2 -> SM traffic per
+// SM halves.  A ring slot is refilled once BOTH CTAs' MMAs on it have retired (multicast commits on w_empty, count 2).
+template <int NET, bool PAIR = false, bool WSHARE = false>
 __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   using S = Sched<NET>;
   static_assert(!PAIR || NET == NET_SPACE, "the CTA-pair protocol is built for the SpaceNet schedule");
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  static_assert(!(PAIR && WSHARE) && (!WSHARE || NET == NET_SPACE), "weight sharing is a SpaceNet-only alternative to the pair protocol");
+  const uint32_t rank = (PAIR || WSHARE) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -647,7 +669,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   constexpr uint32_t STAGE_STRIDE = PAIR ? S::stage_bytes / 2 : S::stage_bytes;
   static_assert(NST <= MAX_STAGE, "barrier slots");
   if (tid == 0) {
-    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), 1); mbar_init(BAR(BAR_WPEER + i), 1); }
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), WSHARE ? 2 : 1); mbar_init(BAR(BAR_WPEER + i), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(BAR(BAR_AREADY + i), N_ARRIVE);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_ARRIVE); }
     mbar_init(BAR(BAR_RAWFULL), 4);          // the four epilogue warps that own the tile's final rows
@@ -657,14 +679,14 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), S::tmem_cols); else tmem_alloc(smem_u32(tmem_slot), S::tmem_cols); }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone arrives on them remotely
+  if (PAIR || WSHARE) cluster_sync_all();        // the peer's barriers exist before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // barrier `i` as the LEADER sees it (what the epilogue warps of either CTA arrive on)
   auto LBAR = [&](int i) { return PAIR ? map_to_cta(BAR(i), 0) : BAR(i); };
   // tiles: CTA b takes tiles b, b + grid, ...; the CTAs of a pair run the same number of rounds (the odd one out gets a tile
   // past the end, whose points are all invalid)
-  auto in_range = [&](long long tile) { return PAIR ? ((tile & ~1LL) < n_tiles) : (tile < n_tiles); };
+  auto in_range = [&](long long tile) { return (PAIR || WSHARE) ? ((tile & ~1LL) < n_tiles) : (tile < n_tiles); };
 
   if (warp == 0) {
     // =============================== weight producer ===============================
@@ -681,6 +703,13 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               if (term == 1 && !split(l)) continue;          // single-pass layers never touch the lo stages
               const uint32_t s = cnt % NST, n = cnt / NST;
               mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
+              if (WSHARE) {      // the whole stage lands here (half from this CTA's copy, half from the peer's); this CTA issues its half to both
+                mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
+                bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), src + rank * (bytes / 2), bytes / 2,
+                            BAR(BAR_WFULL + s), (uint16_t)3);
+                ++cnt;
+                continue;
+              }
               mbar_expect_tx(BAR(BAR_WFULL + s), mine);
               bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, src + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
               ++cnt;
@@ -758,6 +787,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
                   for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
                 }
                 if (PAIR) umma_commit_pair(BAR(BAR_WEMPTY + s));    // ring slot (of both CTAs) reusable once these MMAs retire
+                else if (WSHARE) umma_commit_mc(BAR(BAR_WEMPTY + s), (uint16_t)3);   // ... this CTA's MMAs: one of the two arrivals, in both CTAs
                 else umma_commit(BAR(BAR_WEMPTY + s));
                 ++cnt;
               }
@@ -772,8 +802,8 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     // =============================== compositing warps (coarse-pass fusion) ===============================
     if (P.fuse.on) {
       float* cdf = reinterpret_cast<float*>(smem + S::misc_base + MISC_CDF) + (warp - 2) * 64;
-      if (P.fuse.n2 <= 128) fused_composite_loop<4>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane);
-      else fused_composite_loop<8>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane);
+      if (P.fuse.n2 <= 128) fused_composite_loop<4>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane, WSHARE);
+      else fused_composite_loop<8>(P, s_part, cdf, BAR(BAR_RAWFULL), BAR(BAR_RAWEMPTY), n_tiles, warp - 2, lane, WSHARE);
     }
   } else if (warp >= S::EPI_W0) {
     // =============================== encoding + epilogue warps ===============================
@@ -1003,7 +1033,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   // teardown
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();                  // neither CTA leaves (or frees tensor memory) while the other may still touch it
+  if (PAIR || WSHARE) cluster_sync_all();        // neither CTA leaves (or frees tensor memory) while the other may still touch it
   if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, S::tmem_cols); else tmem_dealloc(tmem_base, S::tmem_cols); }
 }
 
@@ -1452,11 +1482,12 @@ static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   // per-device attribute, set on every launch (one process may drive several devices; cost: microseconds)
   using S = Sched<NET>;
   constexpr bool PAIR = (NET == NET_SPACE) && (SPACE_CTA_PAIR != 0);
-  auto kern = mlp_tc_kernel<NET, PAIR>;
+  constexpr bool WSHARE = (NET == NET_SPACE) && (SPACE_WSHARE != 0) && !PAIR;      // (an odd SM count leaves one SM idle: 148 is even)
+  auto kern = mlp_tc_kernel<NET, PAIR, WSHARE>;
   STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_total));
   if (S::CTAS_PER_SM > 1)     // ask for the largest shared-memory carveout, or the second CTA does not fit next to the first
     STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  if (PAIR) {                 // clusters of two CTAs (one TPC): grid = an even number of CTAs, one per SM
+  if (PAIR || WSHARE) {       // clusters of two CTAs (one TPC): grid = an even number of CTAs, one per SM
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(S::N_THREADS); cfg.dynamicSmemBytes = S::smem_total; cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -184,3 +184,34 @@ def test_flow_reuse_is_not_observable(monkeypatch):
             del model
         for k in outs[True]:
             assert np.array_equal(outs[True][k], outs[False][k]), (name, over, k, float(np.abs(outs[True][k].astype(np.float64) - outs[False][k]).max()))
+
+
+def test_render_host_matches_device_render():
+    """`stnerf_render_host` (the e2e path bench.py times: pinned host rays up and image planes / masks down, chunk by chunk on
+    copy streams while other chunks render) returns exactly what `stnerf_render` leaves on the device for the same rays and seed --
+    several chunks (chunk_rays = 1024), a ragged last chunk, coarse-only calls, staging pre-sized by `stnerf_reserve_host`."""
+    name = "syn_L2_64_128"
+    case = C.CASES[name]
+    model = build_case_model(name, "exact", chunk_rays=1024)
+    dev = torch.device("cuda", 0)
+    nat = model._ensure_native(dev)
+    nat.set_scene(model._resolve_scene(torch.tensor(case["frame_ids"], dtype=torch.float32), 0.3, 0.05))
+    from stnerf_b200 import ops
+    K, T = O.synthetic_camera(4, 16, 50, 75)
+    rays = ops.generate_rays(K, T, 50, 75, frame_ids=case["frame_ids"])          # 3750 rays = 3 full chunks + 678
+    nat.reserve_host(rays.shape[0], rays.shape[1])
+    nat.render(rays[:8], 64, 128, seed=1)                                  # sizes the workspace (stnerf_reserve would too)
+    ws0 = nat.workspace_bytes()
+    rays_host = rays.cpu().pin_memory()
+    for only_coarse in (False, True):
+        out_d, mask_d = nat.render(rays, 64, 128, only_coarse=only_coarse, seed=77)
+        out_h = torch.full((2, 4, 5 * rays.shape[0]), -7.0).pin_memory()
+        mask_h = torch.full((3, rays.shape[0]), 9, dtype=torch.uint8).pin_memory()
+        nat.render_host(rays_host, 64, 128, only_coarse=only_coarse, seed=77, out_host=out_h, mask_host=mask_h)
+        assert torch.equal(mask_h, mask_d.cpu())
+        assert torch.equal(out_h[0], out_d[0].cpu())                       # coarse images of every layer
+        if only_coarse:
+            assert bool((out_h[1] == -7.0).all())                          # fine planes untouched
+        else:
+            assert torch.equal(out_h[1], out_d[1].cpu())
+    assert nat.workspace_bytes() == ws0
