@@ -338,10 +338,10 @@ def roofline_of(wl, res, precision, steps, peaks):
     terms = PRECISION_TERMS[precision]
     traffic, traffic_note = None, None
     try:      # DRAM bytes per point of the same kernel from the committed `ncu --set full` capture, scaled to the mean launch
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_spacenet_traffic.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_spacenet_traffic.json")))
         traffic = cap["dram_bytes_per_point"] * pts / max(1, sp["launches"])
         traffic_note = ("NOT measured in this run: dram__bytes_read+write per point (%.1f B) from the committed ncu --set full capture "
-                        "profiles/r01_spacenet_traffic.json (%s) x this run's mean points per launch" % (cap["dram_bytes_per_point"], cap["kernel"]))
+                        "profiles/r02_spacenet_traffic.json (%s) x this run's mean points per launch" % (cap["dram_bytes_per_point"], cap["kernel"]))
     except Exception:
         pass
     ms_total = res["ms_per_step"] * steps

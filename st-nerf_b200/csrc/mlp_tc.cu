@@ -44,6 +44,9 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
+#ifndef SPACE_ACOLLECT
+#define SPACE_ACOLLECT 0              // 1: split layers issue Ahi*Whi (collector::a::fill), Ahi*Wlo (lastuse), Alo*Whi per k-step: A read twice, not 3x
+#endif
 #ifndef MOTION_CTAS_PER_SM
 #define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
@@ -133,6 +136,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// The same MMA with an A-collector hint: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` takes it from
+// there (the next MMA with the SAME A descriptor does not re-read shared memory) and releases it.
+__device__ __forceinline__ void umma_f16_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_alast(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -768,6 +789,25 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             tc_fence_after();
             for (int sub = 0; sub < 2; ++sub) {
               const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
+              if (SPACE_ACOLLECT && !PAIR && split(l)) {
+                // both stages of this sub-chunk (hi, then lo) at once, so the two products that share Ahi are issued back to back
+                const uint32_t s0 = cnt % NST, n0 = cnt / NST, s1 = (cnt + 1) % NST, n1 = (cnt + 1) / NST;
+                mbar_wait(BAR(BAR_WFULL + s0), n0 & 1);
+                mbar_wait(BAR(BAR_WFULL + s1), n1 & 1);
+                tc_fence_after();
+                const uint32_t whi = sbase + S::ring_base + s0 * STAGE_STRIDE, wlo = sbase + S::ring_base + s1 * STAGE_STRIDE;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t ah = make_desc_sw128(a_hi + a_off + ks * 32), al = make_desc_sw128(a_lo + a_off + ks * 32);
+                  umma_f16_afill(d, ah, make_desc_sw64(whi + ks * 32), idesc, (c == 0 && sub == 0 && ks == 0) ? 0u : 1u);
+                  umma_f16_alast(d, ah, make_desc_sw64(wlo + ks * 32), idesc, 1u);
+                  umma_f16(d, al, make_desc_sw64(whi + ks * 32), idesc, 1u);
+                }
+                if (WSHARE) { umma_commit_mc(BAR(BAR_WEMPTY + s0), (uint16_t)3); umma_commit_mc(BAR(BAR_WEMPTY + s1), (uint16_t)3); }
+                else { umma_commit(BAR(BAR_WEMPTY + s0)); umma_commit(BAR(BAR_WEMPTY + s1)); }
+                cnt += 2;
+                continue;
+              }
               for (int term = 0; term < 2; ++term) {
                 if (term == 1 && !split(l)) continue;
                 const uint32_t s = cnt % NST, n = cnt / NST;
