@@ -18,10 +18,15 @@
 //     (b1 + W1[:,256:] . relu(enc)), so the last GEMM is a clean K=256;
 //   * the 1-wide density head, the 3-wide rgb / flow heads and all biases are fp32 FFMA work in the epilogue.
 //
-// Warp roles (SpaceNet, 384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue /
-// encoding warps: warp%4 selects the TMEM lane quarter (row = 32*(warp%4) + lane), (warp-4)/4 the column half of
-// every 64-column chunk and the half of the encoding frequencies the thread computes for its row.  (MotionNet, 320 threads:
-// the same roles without the two spare warps, epilogue warps 2..9.)
+//   * SpaceNet CTAs run as 2-CTA clusters that share the weight stream: each CTA pulls half of every stage from L2 and multicasts
+//     it into both shared memories (SPACE_WSHARE); tiles, accumulators and MMAs stay per CTA;
+//   * in the coarse pass (n1 = 64: a tile = two whole rays of one layer) two otherwise idle warps composite the tile's rgb / sigma
+//     rows and draw + merge the fine depths (FuseCoarse, resample.cuh): the coarse samples never leave the SM.
+//
+// Warp roles (SpaceNet, 384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 2..3 = compositing warps
+// (coarse-pass fusion), warps 4..11 = epilogue / encoding warps: warp%4 selects the TMEM lane quarter (row = 32*(warp%4) + lane),
+// (warp-4)/4 the column half of every 64-column chunk and the half of the encoding frequencies the thread computes for its row.
+// (MotionNet, 320 threads: the same roles without warps 2..3, epilogue warps 2..9.)
 //
 // Build flags: SPACE_WSHARE=0 switches the shared weight stream off (every CTA then pulls all 1.8 MB per tile from L2 itself);
 // SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not faster: DESIGN.md 8);
