@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- rays/sec of the layered ray-march hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision exact|mixed|fp32|fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision exact|exact_cf|mixed|fp32|fast]
                     [--workload taekwondo2|walking4|walking6_4k] [--no-extra] [--no-cpu-baseline]
 
 Workload (BASELINE.json configs[1]): taekwondo 2-layer scene, 1080p, 16 views, 64 coarse + 128 fine samples.
@@ -55,8 +55,9 @@ WORKLOADS = {
                         frame_ids=[0.0, 30.0, 31.0, 32.0, 33.0, 34.0, 35.0], fixture="scale_walk6_4k",
                         name="walking 6-layer 4K, 32 views, 64+192 samples (BASELINE configs[4])"),
 }
-PRECISION_TERMS = {"exact": 3.0, "mixed": 3.0 - 2.0 * (256 * 128) / 462336.0, "fast": 1.0, "fp32": 1.0}
-DTYPES = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32", "fast": "f16 products, f32 accumulate",
+PRECISION_TERMS = {"exact": 3.0, "exact_cf": 3.0, "mixed": 3.0 - 2.0 * (256 * 128) / 462336.0, "fast": 1.0, "fp32": 1.0}
+DTYPES = {"exact": "f32 via fp16x3 split products (tcgen05), f32 accumulate", "fp32": "f32",
+          "exact_cf": "f32 via fp16x3 split products (tcgen05), correction products first in the coarse pass and the MotionNets, f32 accumulate", "fast": "f16 products, f32 accumulate",
           "mixed": "f32 via fp16x3 split products on everything the density depends on, single f16 pass on the colour-only layer "
                    "rgb_net.1 (tcgen05), f32 accumulate"}
 
@@ -193,7 +194,7 @@ def cpu_reference_rate(wl, steps, warmup, rays_per_worker):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_leg_parity(wl, model, dev):
+def cpu_leg_parity(wl, model, dev, precision="exact"):
     """Checker of the CPU leg (rank 0, N = 1): the committed fixture of the UNMODIFIED reference for this workload
     (tests/golden/scale_*.npz: 16 384 / 4 096 rays of a full-size view, injected uniforms; inputs regenerated by the test
     infrastructure's seeded generator) against the GPU path in the bench's precision mode."""
@@ -205,16 +206,26 @@ def cpu_leg_parity(wl, model, dev):
     if gold is None:
         return None
     rays, jit, u = C.scale_inputs(case)
-    model.inject_uniforms(jit.to(dev).contiguous(), u.to(dev).contiguous())
-    with torch.no_grad():
-        out = model(rays.to(dev), None, None, density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
-    got = out[0][0].float().cpu().numpy()
     ref = gold["fine_mixed.rgb"]
-    err = np.abs(got - ref).max(1)
-    mse = float(((got.astype(np.float64) - ref) ** 2).mean())
-    return {"rays": int(rays.shape[0]), "max_abs_rgb_err": float(err.max()), "frac_pixels_over_1e-3": float((err > 1e-3).mean()),
-            "pixels_over_1e-3": int((err > 1e-3).sum()), "median_abs_rgb_err": float(np.median(err)),
-            "psnr_db": 99.0 if mse == 0 else float(10.0 * math.log10(1.0 / mse)),
+
+    def one():
+        model.inject_uniforms(jit.to(dev).contiguous(), u.to(dev).contiguous())
+        with torch.no_grad():
+            out = model(rays.to(dev), None, None, density_threshold=case["thr"][0], bkgd_density_threshold=case["thr"][1])
+        got = out[0][0].float().cpu().numpy()
+        err = np.abs(got - ref).max(1)
+        mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+        return {"max_abs_rgb_err": float(err.max()), "frac_pixels_over_1e-3": float((err > 1e-3).mean()),
+                "pixels_over_1e-3": int((err > 1e-3).sum()), "median_abs_rgb_err": float(np.median(err)),
+                "psnr_db": 99.0 if mse == 0 else float(10.0 * math.log10(1.0 / mse))}
+
+    rep = one()
+    other = None
+    if precision == "exact":       # the opt-in accuracy variant on the same fixture (STNERF_PREC_TC_3XF16_CF; not the timed mode)
+        model.set_precision("exact_cf")
+        other = one()
+        model.set_precision("exact")
+    return {"rays": int(rays.shape[0]), **rep, "same_fixture_in_exact_cf_mode": other,
             "against": "unmodified reference LayeredRFRender.forward on CPU (fixture tests/golden/%s.npz), identical rays / weights / "
                        "uniforms; every ray over 1e-3 is attributed (fine-sample placement within the reference's own conditioning, or an "
                        "instability of the reference) in tests/test_gpu_parity_scale.py" % wl["fixture"]}
@@ -317,7 +328,7 @@ def measure(wl, precision, steps, warmup, rank, world, local_rank, want_e2e=True
                       "api": "stnerf_render_host (C-ABI, pinned host buffers; rays up and image planes down chunk by chunk on copy "
                              "streams while other chunks render), %d steps, max over ranks of the host wall clock" % steps}
     if parity_fn is not None and rank == 0:
-        res["parity"] = parity_fn(wl, model, dev)
+        res["parity"] = parity_fn(wl, model, dev, precision)
     del svr, model
     torch.cuda.empty_cache()
     return res
@@ -369,7 +380,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="exact", choices=["exact", "mixed", "fp32", "fast"])
+    ap.add_argument("--precision", default="exact", choices=["exact", "exact_cf", "mixed", "fp32", "fast"])
     ap.add_argument("--cpu-sample-rays", type=int, default=1024, help="rays per CPU worker per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")

@@ -46,9 +46,15 @@ enum {
   STNERF_PREC_TC_3XF16 = 1,    /* tcgen05 fp16 3-term split (hi*hi + lo*hi + hi*lo), fp32 accumulate:     */
                                /* ~fp32 products, meets the 1e-3 RGB gate               */
   STNERF_PREC_TC_F16 = 2,      /* tcgen05 single fp16 pass: fastest, does NOT meet the 1e-3 gate          */
-  STNERF_PREC_TC_MIXED = 3     /* TC_3XF16 for everything the density depends on (SpaceNet trunk + sigma head, MotionNet); */
+  STNERF_PREC_TC_MIXED = 3,    /* TC_3XF16 for everything the density depends on (SpaceNet trunk + sigma head, MotionNet); */
                                /* single fp16 pass for the colour-only layer rgb_net.1 (spacenet.py:81-86): ~5 % fewer     */
                                /* MMAs, colour error <= 2.5e-4, resampling untouched -- inside the 1e-3 gate               */
+  STNERF_PREC_TC_3XF16_CF = 4  /* TC_3XF16 with the two correction products of every layer issued FIRST (over the whole K  */
+                               /* range, then hi*hi) in the coarse pass and the MotionNets -- what the sample placement    */
+                               /* depends on.  The tensor core truncates when it adds into its fp32 accumulator; this      */
+                               /* order truncates at full magnitude K/16 instead of 3K/16 times: sigma error / 3 (2e-6 rel */
+                               /* rms, the reference's own fp32 noise is 1e-6), about half the rays over the 1e-3 gate at  */
+                               /* scale; the hi weight stages stream twice (cost: see DESIGN 3.1)                          */
 };
 
 typedef struct stnerf_ctx* stnerf_handle;

@@ -68,6 +68,11 @@ struct stnerf_ctx {
   std::vector<cudaEvent_t> ev_pool;                         // timing-disabled events, reused call after call
   float* box_table = nullptr;  // [n_frames][l][2][3] per-frame boxes for rays with their own frame id (stnerf_set_box_table)
   int box_frames = 0;
+  // Order of the split MMAs (mlp_tc.cu): 0 = interleaved everywhere, 1 = correction products first in the COARSE pass and in the
+  // MotionNets (what the sample placement and the positions depend on), interleaved in the fine SpaceNet pass, 2 = first everywhere.
+  // -1 (default): by precision -- STNERF_PREC_TC_3XF16_CF means 1, every other mode 0.
+  int lo_first_env = -1;       // STNERF_LO_FIRST=0|1|2 in the environment at create overrides (A/B: profiles/r02_ab_lo_first.json)
+  int lo_first_mode() const { return lo_first_env >= 0 ? lo_first_env : (precision == STNERF_PREC_TC_3XF16_CF ? 1 : 0); }
   bool no_fuse = false;        // STNERF_NO_FUSE=1 in the environment at create: keep the coarse compositing in its own kernel (A/B)
   int* any_frac = nullptr;     // scratch flag for stnerf_motionnet(lerp_mode=-1)
   RayIdMap idmap{0, 0, 0};     // stnerf_set_ray_ids
@@ -171,7 +176,7 @@ uint64_t stnerf_launch_count(void) { return g_launches.load(); }
 
 int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   if (!out || !d || d->n_layers < 2 || d->n_layers > STNERF_MAX_LAYERS) return STNERF_EINVAL;
-  if (d->precision < 0 || d->precision > STNERF_PREC_TC_MIXED || d->chunk_rays < 0) return STNERF_EINVAL;
+  if (d->precision < 0 || d->precision > STNERF_PREC_TC_3XF16_CF || d->chunk_rays < 0) return STNERF_EINVAL;
   // the kernels index samples of a chunk with 32-bit integers: chunk_rays * STNERF_MAX_S must stay below 2^31
   if ((long long)d->chunk_rays * STNERF_MAX_S >= (1LL << 31)) return STNERF_EINVAL;
   int ndev = 0;
@@ -190,6 +195,7 @@ int stnerf_create(stnerf_handle* out, const stnerf_model_desc* d) {
   c->precision = d->precision;
   c->chunk_rays = d->chunk_rays > 0 ? d->chunk_rays : 65536;
   if (const char* e = getenv("STNERF_NO_FUSE")) c->no_fuse = (e[0] == '1');
+  if (const char* e = getenv("STNERF_LO_FIRST")) c->lo_first_env = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
   if (const char* e = getenv("STNERF_NO_REUSE")) c->no_reuse = (e[0] == '1');
   if (cudaMalloc((void**)&c->any_frac, 4) != cudaSuccess) { delete c; return STNERF_ENOMEM; }
   *out = c;
@@ -213,7 +219,7 @@ void stnerf_destroy(stnerf_handle c) {
 }
 
 int stnerf_set_precision(stnerf_handle c, int precision) {
-  if (!c || precision < 0 || precision > STNERF_PREC_TC_MIXED) return STNERF_EINVAL;
+  if (!c || precision < 0 || precision > STNERF_PREC_TC_3XF16_CF) return STNERF_EINVAL;
   c->precision = precision;
   return STNERF_OK;
 }
@@ -311,7 +317,7 @@ int stnerf_load_motionnet(stnerf_handle c, int layer, const float* blob, size_t 
 // ---- packed-weight image: every loaded network's device buffers, as they are, behind a small header ----
 namespace {
 constexpr char PACK_MAGIC[8] = {'S', 'T', 'N', 'B', '2', '0', '0', 'W'};
-constexpr uint32_t PACK_VERSION = 1;
+constexpr uint32_t PACK_VERSION = 2;      // 2: weight stream = correction section + main section per layer
 struct PackHeader { char magic[8]; uint32_t version, n_layers, n_records, reserved; };
 struct PackRec { uint32_t kind, fine, layer, use_time; uint64_t simt_floats, stream_bytes, aux_floats, tail_floats; float scalars[4]; uint32_t pad[4]; };
 static size_t rec_payload(const PackRec& r) { return r.simt_floats * 4 + r.stream_bytes + r.aux_floats * 4 + r.tail_floats * 4; }
@@ -463,7 +469,7 @@ static void fill_edit(PointSrc& s, const stnerf_scene& sc, int layer, bool fine)
 }
 
 static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, float* raw, float* rgb, float* sigma,
-                        cudaStream_t st, int count_slot = -1, const FuseCoarse* fuse = nullptr) {
+                        cudaStream_t st, int count_slot = -1, const FuseCoarse* fuse = nullptr, bool fine_pass = false) {
   if (!net.loaded) return STNERF_ENOWEIGHTS;
   ProfScope ps(c, 0, (double)src.n_slots * src.S, count_slot, src.S, st);
   if (c->precision == STNERF_PREC_FP32_SIMT)
@@ -471,11 +477,12 @@ static int run_spacenet(stnerf_ctx* c, const PointSrc& src, SpaceNetDev& net, fl
   if (src.mode == SRC_EXPLICIT) {      // unit entry point: one bias row per point, stream-ordered scratch
     float* cb = nullptr;
     STNERF_CUDA(cudaMallocAsync((void**)&cb, (size_t)std::max<long long>(src.n_slots, 1) * 128 * sizeof(float), st));
-    const int rc = tc_launch_spacenet(src, net.tc, net.w, c->precision, cb, raw, rgb, sigma, c->num_sms, st);
+    const int rc = tc_launch_spacenet(src, net.tc, net.w, c->precision, cb, raw, rgb, sigma, c->num_sms, st, nullptr, c->lo_first_mode() != 0);
     STNERF_CUDA(cudaFreeAsync(cb, st));
     return rc;
   }
-  return tc_launch_spacenet(src, net.tc, net.w, c->precision, c->cbuf, raw, rgb, sigma, c->num_sms, st, fuse);
+  const int lo_first = c->lo_first_mode() == 2 || (c->lo_first_mode() == 1 && !fine_pass);
+  return tc_launch_spacenet(src, net.tc, net.w, c->precision, c->cbuf, raw, rgb, sigma, c->num_sms, st, fuse, lo_first);
 }
 static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, const int* lerp_flag, int lerp_force,
                          float* xyz_out, float* flow_out, cudaStream_t st, int count_slot = -1) {
@@ -483,7 +490,8 @@ static int run_motionnet(stnerf_ctx* c, const PointSrc& src, MotionNetDev& net, 
   ProfScope ps(c, 1, (double)src.n_slots * src.S, count_slot, src.S, st);
   if (c->precision == STNERF_PREC_FP32_SIMT)
     return launch_motionnet_simt(src, net.w, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st);
-  return tc_launch_motionnet(src, net.tc, net.w, c->precision, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st);
+  return tc_launch_motionnet(src, net.tc, net.w, c->precision, lerp_flag, lerp_force, xyz_out, flow_out, c->num_sms, st,
+                             c->lo_first_mode() != 0);
 }
 
 // `fuse` (coarse pass only): template of the per-layer fusion request (everything but the layer-specific fields), or null.
@@ -522,7 +530,7 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     int rc;
     if (i == 0) {
       s.hit = nullptr; s.count = nullptr; s.n_slots = n;
-      rc = run_spacenet(c, s, c->space[fine ? 1 : 0][0], raw, nullptr, nullptr, st, -1, fuse ? &f : nullptr);
+      rc = run_spacenet(c, s, c->space[fine ? 1 : 0][0], raw, nullptr, nullptr, st, -1, fuse ? &f : nullptr, fine);
       if (rc) return rc;
       continue;
     }
@@ -544,7 +552,7 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
       s.pos2 = xyz_out;
       s.src_map = c->src_map + (size_t)i * R * c->cap_s2;
       s.n_first = reuse_n1;
-      rc = run_spacenet(c, s, c->space[1][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1, nullptr);
+      rc = run_spacenet(c, s, c->space[1][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1, nullptr, true);
       if (rc) return rc;
       continue;
     }
@@ -553,7 +561,7 @@ static int run_nets(stnerf_ctx* c, const float* rays, long long n, int ray_strid
     s.mode = SRC_XYZ;
     s.pos = xyz_out;
     rc = run_spacenet(c, s, c->space[fine ? 1 : 0][i], raw, nullptr, nullptr, st, chunk_slot >= 0 ? chunk_slot * 8 + i : -1,
-                      fuse ? &f : nullptr);
+                      fuse ? &f : nullptr, fine);
     if (rc) return rc;
   }
   return STNERF_OK;

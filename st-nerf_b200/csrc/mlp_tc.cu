@@ -1,4 +1,5 @@
-// tcgen05 / TMEM evaluation of SpaceNet and MotionNet (precision modes TC_3XF16 "exact", TC_MIXED "mixed", TC_F16 "fast").
+// tcgen05 / TMEM evaluation of SpaceNet and MotionNet (precision modes TC_3XF16 "exact", TC_3XF16_CF "exact_cf", TC_MIXED "mixed",
+// TC_F16 "fast").
 //
 // Persistent CTAs (SpaceNet: one per SM; MotionNet: two per SM, see Sched<NET_MOTION>) walk tiles of 128 points.  Per tile the
 // whole network runs on-chip:
@@ -10,9 +11,14 @@
 //   * every MMA is M=128 x N=256 (or 128) x K=16, so the A tile is re-read from shared memory once per 256 outputs;
 //   * accumulators live in TMEM (two 128x256 fp32 buffers = all 512 columns) so the epilogue of layer k
 //     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1, k-chunk by k-chunk;
-//   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which
-//     reproduces fp32 products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate);
-//     mixed mode keeps that everywhere the density depends on and runs the colour-only layer rgb_net.1 in one pass;
+//   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which reproduces fp32
+//     products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate); mixed mode keeps that
+//     everywhere the density depends on and runs the colour-only layer rgb_net.1 in one pass;
+//   * order of the three products (template parameter LOFIRST): interleaved per 32-k sub-chunk (default: every weight stage is
+//     streamed once), or -- TC_3XF16_CF "exact_cf", coarse pass + MotionNets -- the two correction products FIRST over the whole K
+//     range, then Ahi*Whi.  The tensor core truncates when it adds into its fp32 accumulator (stnerf_selftest_umma_accum), an
+//     error relative to the accumulator's magnitude at that moment; corrections-first truncates at full magnitude K/16 instead
+//     of 3K/16 times per layer (sigma error 7e-6 -> 2e-6 rel. rms) and streams the hi weight stages twice (+2.5 % per step);
 //   * the input encoding of tile i+1 is written while the tensor core works on the late layers of tile i;
 //   * relu(PE(dir) | PE(time)) enters rgb_net.1 as a per-ray fp32 bias computed by head_bias_kernel
 //     (b1 + W1[:,256:] . relu(enc)), so the last GEMM is a clean K=256;
@@ -49,9 +55,6 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
-#ifndef SPACE_ACOLLECT
-#define SPACE_ACOLLECT 0              // 1: split layers issue Ahi*Whi (collector::a::fill), Ahi*Wlo (lastuse), Alo*Whi per k-step: A read twice, not 3x
-#endif
 #ifndef MOTION_CTAS_PER_SM
 #define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
@@ -141,24 +144,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// The same MMA with an A-collector hint: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` takes it from
-// there (the next MMA with the SAME A descriptor does not re-read shared memory) and releases it.
-__device__ __forceinline__ void umma_f16_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_alast(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -316,7 +301,7 @@ template <int NET>
 __host__ __device__ constexpr size_t stream_bytes_per_tile() {
   size_t n = 0;
   for (int l = 0; l < Sched<NET>::N_LAYERS; ++l)
-    n += (size_t)(Sched<NET>::act_chunks(l) + Sched<NET>::enc_chunks(l)) * 2 /*sub-chunks*/ * 2 /*hi,lo*/ *
+    n += (size_t)(Sched<NET>::act_chunks(l) + Sched<NET>::enc_chunks(l)) * 2 /*sub-chunks*/ * 3 /*correction pass: hi, lo; main pass: hi*/ *
          Sched<NET>::n_out(l) * 64;
   return n;
 }
@@ -329,6 +314,10 @@ struct TcParams {
   const float* cbuf;          // SpaceNet: per-slot rgb_net.1 bias (b1 + W1[:,256:].relu(enc(dir,time))), [slots][128]
   int exact;                  // 1: 3-term split, 0: single fp16 pass
   int single_last;            // with exact: the LAST GEMM layer (SpaceNet rgb_net.1, colour branch only) runs a single pass
+  int lo_first;               // split layers (selects the kernel instantiation): 0 = interleaved per 32-k sub-chunk (default: hi stages
+                              // streamed once); 1 = correction products first over the whole K range, then Ahi*Whi (fewer truncations
+                              // at full magnitude, sigma error / 3; hi weight stages streamed twice: measured -7 % when used in the
+                              // coarse pass + MotionNets only)
   // outputs
   float* raw;                 // float4 per sample (pipeline mode)
   float* rgb_out;             // explicit mode
@@ -662,7 +651,7 @@ __device__ __noinline__ void fused_composite_loop(const TcParams& P, const float
 // WSHARE: the two CTAs of a cluster keep their own tiles, accumulators and MMAs (cta_group::1) but share the WEIGHT STREAM: CTA r
 // pulls rows [r*N/2, (r+1)*N/2) of every stage from L2 and multicasts them into both shared memories, so the L2 -> SM traffic per
 // SM halves.  A ring slot is refilled once BOTH CTAs' MMAs on it have retired (multicast commits on w_empty, count 2).
-template <int NET, bool PAIR = false, bool WSHARE = false>
+template <int NET, bool PAIR = false, bool WSHARE = false, bool LOFIRST = false>
 __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   using S = Sched<NET>;
   static_assert(!PAIR || NET == NET_SPACE, "the CTA-pair protocol is built for the SpaceNet schedule");
@@ -685,6 +674,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   // 3-term split for layer l?  (mixed mode: everything the density depends on is split, the colour-only layer is not)
   const bool single_last = P.single_last != 0;
   auto split = [&](int l) { return exact && !(single_last && l == S::N_LAYERS - 1); };
+  constexpr bool lo_first = LOFIRST;      // order of the split MMAs: a compile-time variant, the interleaved default pays nothing for it
   const long long n_points = src_num_points(P.src);
   const long long n_tiles = (n_points + TILE_M - 1) / TILE_M;
 
@@ -724,22 +714,46 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
           const uint32_t bytes = (uint32_t)S::n_out(l) * 64;
           const uint32_t mine = PAIR ? bytes / 2 : bytes;     // pair: the rows of this CTA's half of the output columns
-          for (int sc = 0; sc < nsub; ++sc)
-            for (int term = 0; term < 2; ++term, src += bytes) {
-              if (term == 1 && !split(l)) continue;          // single-pass layers never touch the lo stages
+          // a layer of the stream = correction section [(hi, lo) per 32-k sub-chunk] + main section [hi per sub-chunk] (see the MMA warp)
+          if (!LOFIRST) {     // interleaved order: the (hi, lo) stages of the correction section serve all three products
+            for (int sc = 0; sc < nsub; ++sc)
+              for (int term = 0; term < 2; ++term, src += bytes) {
+                if (term == 1 && !split(l)) continue;          // single-pass layers never touch the lo stages
+                const uint32_t s = cnt % NST, n = cnt / NST;
+                mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
+                if (WSHARE) {      // the whole stage lands here (half from this CTA's copy, half from the peer's); this CTA issues its half to both
+                  mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
+                  bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), src + rank * (bytes / 2), bytes / 2,
+                              BAR(BAR_WFULL + s), (uint16_t)3);
+                  ++cnt;
+                  continue;
+                }
+                mbar_expect_tx(BAR(BAR_WFULL + s), mine);
+                bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, src + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
+                ++cnt;
+              }
+            src += (size_t)nsub * bytes;      // the main section is not used
+          } else {
+            auto LOAD = [&](const uint8_t* stage) {
               const uint32_t s = cnt % NST, n = cnt / NST;
               mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
               if (WSHARE) {      // the whole stage lands here (half from this CTA's copy, half from the peer's); this CTA issues its half to both
                 mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
-                bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), src + rank * (bytes / 2), bytes / 2,
+                bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), stage + rank * (bytes / 2), bytes / 2,
                             BAR(BAR_WFULL + s), (uint16_t)3);
-                ++cnt;
-                continue;
+              } else {
+                mbar_expect_tx(BAR(BAR_WFULL + s), mine);
+                bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, stage + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
               }
-              mbar_expect_tx(BAR(BAR_WFULL + s), mine);
-              bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, src + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
               ++cnt;
-            }
+            };
+            const uint8_t* corr = src;
+            const uint8_t* mainp = src + (size_t)nsub * 2 * bytes;
+            if (split(l))
+              for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc) * bytes); LOAD(corr + (size_t)(2 * sc + 1) * bytes); }
+            for (int sc = 0; sc < nsub; ++sc) LOAD(mainp + (size_t)sc * bytes);
+            src = mainp + (size_t)nsub * bytes;
+          }
         }
       }
     }
@@ -750,14 +764,13 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x)
         for (int l = 0; l < S::N_LAYERS; ++l) {
           const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
-          for (int sc = 0; sc < nsub; ++sc)
-            for (int term = 0; term < 2; ++term) {
-              if (term == 1 && !split(l)) continue;
-              const uint32_t s = cnt % NST, n = cnt / NST;
-              mbar_wait(BAR(BAR_WFULL + s), n & 1);
-              mbar_arrive_cluster(map_to_cta(BAR(BAR_WPEER + s), 0));
-              ++cnt;
-            }
+          const int nstages = split(l) ? (lo_first ? 3 : 2) * nsub : nsub;
+          for (int k = 0; k < nstages; ++k) {
+            const uint32_t s = cnt % NST, n = cnt / NST;
+            mbar_wait(BAR(BAR_WFULL + s), n & 1);
+            mbar_arrive_cluster(map_to_cta(BAR(BAR_WPEER + s), 0));
+            ++cnt;
+          }
         }
     }
   } else if (warp == 1) {
@@ -775,67 +788,109 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const uint32_t d = tmem_base + b * S::d_stride;
           const uint32_t idesc = PAIR ? idesc_pair_n((uint32_t)S::n_out(l)) : idesc_n((uint32_t)S::n_out(l));
           const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
-          for (int c = 0; c < nch; ++c) {
-            uint32_t a_hi, a_lo;
-            if (c < nact) {
-              a_hi = sbase + S::act_base + c * ABLOCK;
-              a_lo = a_hi + S::LO_STRIDE;
-              WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1);
-              ++a_uses[c];
-            } else {
-              const int e = c - nact;
-              a_hi = sbase + S::enc_base + e * ABLOCK;
-              a_lo = a_hi + S::ENC_LO_STRIDE;
-              if (l == 0 && e == 0) {                              // one arrival phase per tile covers the whole encoding
-                WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
-                ++a_uses[4];
+          if (!LOFIRST) {
+            // interleaved order: per 32-k sub-chunk, Ahi*Whi and Alo*Whi off the hi stage, Ahi*Wlo off the lo stage
+            for (int c = 0; c < nch; ++c) {
+              uint32_t a_hi, a_lo;
+              if (c < nact) {
+                a_hi = sbase + S::act_base + c * ABLOCK;
+                a_lo = a_hi + S::LO_STRIDE;
+                WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1);
+                ++a_uses[c];
+              } else {
+                const int e = c - nact;
+                a_hi = sbase + S::enc_base + e * ABLOCK;
+                a_lo = a_hi + S::ENC_LO_STRIDE;
+                if (l == 0 && e == 0) {                              // one arrival phase per tile covers the whole encoding
+                  WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
+                  ++a_uses[4];
+                }
+              }
+              tc_fence_after();
+              for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
+                for (int term = 0; term < 2; ++term) {
+                  if (term == 1 && !split(l)) continue;
+                  const uint32_t s = cnt % NST, n = cnt / NST;
+                  mbar_wait(BAR(BAR_WFULL + s), n & 1);
+                  if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);      // ... and the peer's half
+                  tc_fence_after();
+                  const uint32_t wsm = sbase + S::ring_base + s * STAGE_STRIDE;
+                  // hi stage: D += Ahi*Whi (+ Alo*Whi);  lo stage: D += Ahi*Wlo
+                  auto MMA = [&](uint32_t a_addr, int ks, uint32_t acc) {
+                    if (PAIR) umma_f16_pair(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+                    else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+                  };
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
+                  if (term == 0 && split(l)) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
+                  }
+                  if (PAIR) umma_commit_pair(BAR(BAR_WEMPTY + s));    // ring slot (of both CTAs) reusable once these MMAs retire
+                  else if (WSHARE) umma_commit_mc(BAR(BAR_WEMPTY + s), (uint16_t)3);   // ... this CTA's MMAs: one of the two arrivals, in both CTAs
+                  else umma_commit(BAR(BAR_WEMPTY + s));
+                  ++cnt;
+                }
               }
             }
-            tc_fence_after();
-            for (int sub = 0; sub < 2; ++sub) {
-              const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
-              if (SPACE_ACOLLECT && !PAIR && split(l)) {
-                // both stages of this sub-chunk (hi, then lo) at once, so the two products that share Ahi are issued back to back
-                const uint32_t s0 = cnt % NST, n0 = cnt / NST, s1 = (cnt + 1) % NST, n1 = (cnt + 1) / NST;
-                mbar_wait(BAR(BAR_WFULL + s0), n0 & 1);
-                mbar_wait(BAR(BAR_WFULL + s1), n1 & 1);
-                tc_fence_after();
-                const uint32_t whi = sbase + S::ring_base + s0 * STAGE_STRIDE, wlo = sbase + S::ring_base + s1 * STAGE_STRIDE;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t ah = make_desc_sw128(a_hi + a_off + ks * 32), al = make_desc_sw128(a_lo + a_off + ks * 32);
-                  umma_f16_afill(d, ah, make_desc_sw64(whi + ks * 32), idesc, (c == 0 && sub == 0 && ks == 0) ? 0u : 1u);
-                  umma_f16_alast(d, ah, make_desc_sw64(wlo + ks * 32), idesc, 1u);
-                  umma_f16(d, al, make_desc_sw64(whi + ks * 32), idesc, 1u);
+          } else {
+            // Order of the MMAs of a layer.  The tensor core TRUNCATES when it adds into the fp32 accumulator (measured:
+            // stnerf_selftest_umma_accum), an error relative to the accumulator's magnitude at that moment.  So the two correction
+            // products go FIRST, over the whole K range, while the accumulator only holds terms 2^-11 of its final size; the main
+            // product Ahi*Whi follows.  A layer then truncates at full magnitude K/16 times instead of 3K/16 times; the price is a
+            // second copy of the hi weight stages in the stream (main section).
+            bool first = true;
+            auto chunk = [&](int c, bool wait, uint32_t& a_hi, uint32_t& a_lo) {
+              if (c < nact) {
+                a_hi = sbase + S::act_base + c * ABLOCK;
+                a_lo = a_hi + S::LO_STRIDE;
+                if (wait) { WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1); ++a_uses[c]; }
+              } else {
+                const int e = c - nact;
+                a_hi = sbase + S::enc_base + e * ABLOCK;
+                a_lo = a_hi + S::ENC_LO_STRIDE;
+                if (wait && l == 0 && e == 0) {                      // one arrival phase per tile covers the whole encoding
+                  WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
+                  ++a_uses[4];
                 }
-                if (WSHARE) { umma_commit_mc(BAR(BAR_WEMPTY + s0), (uint16_t)3); umma_commit_mc(BAR(BAR_WEMPTY + s1), (uint16_t)3); }
-                else { umma_commit(BAR(BAR_WEMPTY + s0)); umma_commit(BAR(BAR_WEMPTY + s1)); }
-                cnt += 2;
-                continue;
               }
-              for (int term = 0; term < 2; ++term) {
-                if (term == 1 && !split(l)) continue;
-                const uint32_t s = cnt % NST, n = cnt / NST;
-                mbar_wait(BAR(BAR_WFULL + s), n & 1);
-                if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);      // ... and the peer's half
-                tc_fence_after();
-                const uint32_t wsm = sbase + S::ring_base + s * STAGE_STRIDE;
-                // hi stage: D += Ahi*Whi (+ Alo*Whi);  lo stage: D += Ahi*Wlo
-                auto MMA = [&](uint32_t a_addr, int ks, uint32_t acc) {
-                  if (PAIR) umma_f16_pair(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
-                  else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
-                };
+              if (wait) tc_fence_after();
+            };
+            // the next weight stage of the stream times the 32-k slice at a_addr
+            auto STAGE = [&](uint32_t a_addr) {
+              const uint32_t s = cnt % NST, n = cnt / NST;
+              mbar_wait(BAR(BAR_WFULL + s), n & 1);
+              if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);        // ... and the peer's half
+              tc_fence_after();
+              const uint32_t wsm = sbase + S::ring_base + s * STAGE_STRIDE;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
-                if (term == 0 && split(l)) {
-#pragma unroll
-                  for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t acc = first ? 0u : 1u;
+                first = false;
+                if (PAIR) umma_f16_pair(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+                else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
+              }
+              if (PAIR) umma_commit_pair(BAR(BAR_WEMPTY + s));        // ring slot (of both CTAs) reusable once these MMAs retire
+              else if (WSHARE) umma_commit_mc(BAR(BAR_WEMPTY + s), (uint16_t)3);   // this CTA's MMAs: one of the two arrivals, in both CTAs
+              else umma_commit(BAR(BAR_WEMPTY + s));
+              ++cnt;
+            };
+            const bool sp = split(l);
+            if (sp) {
+              for (int c = 0; c < nch; ++c) {
+                uint32_t a_hi, a_lo;
+                chunk(c, true, a_hi, a_lo);
+                for (int sub = 0; sub < 2; ++sub) {                  // correction pass: D = Alo*Whi + Ahi*Wlo
+                  STAGE(a_lo + (uint32_t)sub * 64);                  // hi weight stage
+                  STAGE(a_hi + (uint32_t)sub * 64);                  // lo weight stage
                 }
-                if (PAIR) umma_commit_pair(BAR(BAR_WEMPTY + s));    // ring slot (of both CTAs) reusable once these MMAs retire
-                else if (WSHARE) umma_commit_mc(BAR(BAR_WEMPTY + s), (uint16_t)3);   // ... this CTA's MMAs: one of the two arrivals, in both CTAs
-                else umma_commit(BAR(BAR_WEMPTY + s));
-                ++cnt;
               }
+            }
+            for (int c = 0; c < nch; ++c) {                          // main pass: D += Ahi*Whi
+              uint32_t a_hi, a_lo;
+              chunk(c, !sp, a_hi, a_lo);
+              for (int sub = 0; sub < 2; ++sub) STAGE(a_hi + (uint32_t)sub * 64);
             }
           }
           if (PAIR) umma_commit_pair(BAR(BAR_DFULL + b));           // accumulator of layer g complete (in both CTAs)
@@ -1313,6 +1368,7 @@ int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vec
   std::vector<uint8_t> stream;
   for (const LayerSpec& L : layers) {
     const size_t stage = (size_t)L.N * 64;
+    std::vector<uint8_t> main_section;            // the hi stages again, consumed by the main pass (Ahi*Whi) after the correction pass
     for (const auto& ch : L.chunks)
       for (int sub = 0; sub < 2; ++sub) {
         std::vector<uint8_t> hi(stage, 0), lo(stage, 0);
@@ -1327,9 +1383,11 @@ int pack_stream(TcNet& net, const std::vector<LayerSpec>& layers, const std::vec
             memcpy(hi.data() + off, &h, 2);
             memcpy(lo.data() + off, &l, 2);
           }
-        stream.insert(stream.end(), hi.begin(), hi.end());
+        stream.insert(stream.end(), hi.begin(), hi.end());          // correction section: (hi, lo) per 32-k sub-chunk
         stream.insert(stream.end(), lo.begin(), lo.end());
+        main_section.insert(main_section.end(), hi.begin(), hi.end());
       }
+    stream.insert(stream.end(), main_section.begin(), main_section.end());
   }
   if (stream.size() != expect_bytes) return STNERF_EINVAL;
   tc_free(net);
@@ -1522,13 +1580,13 @@ int tc_selftest_pair(float* max_err_host) {
   return STNERF_OK;
 }
 
-template <int NET>
-static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
+template <int NET, bool LOFIRST>
+static int launch_tc_variant(const TcParams& P, int num_sms, cudaStream_t st) {
   // per-device attribute, set on every launch (one process may drive several devices; cost: microseconds)
   using S = Sched<NET>;
   constexpr bool PAIR = (NET == NET_SPACE) && (SPACE_CTA_PAIR != 0);
   constexpr bool WSHARE = (NET == NET_SPACE) && (SPACE_WSHARE != 0) && !PAIR;      // (an odd SM count leaves one SM idle: 148 is even)
-  auto kern = mlp_tc_kernel<NET, PAIR, WSHARE>;
+  auto kern = mlp_tc_kernel<NET, PAIR, WSHARE, LOFIRST>;
   STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_total));
   if (S::CTAS_PER_SM > 1)     // ask for the largest shared-memory carveout, or the second CTA does not fit next to the first
     STNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1548,10 +1606,15 @@ static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
   return STNERF_OK;
 }
 
+template <int NET>
+static int launch_tc(const TcParams& P, int num_sms, cudaStream_t st) {
+  return P.lo_first ? launch_tc_variant<NET, true>(P, num_sms, st) : launch_tc_variant<NET, false>(P, num_sms, st);
+}
+
 bool tc_can_fuse_coarse(int n1, int n2) { return SPACE_CTA_PAIR == 0 && n1 == 64 && n2 >= 1 && n2 <= 256; }
 
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, int precision, float* cbuf, float* raw,
-                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse) {
+                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse, int lo_first) {
   if (!net.blob || !net.w_tail) return STNERF_ENOWEIGHTS;
   if (!cbuf) return STNERF_EINVAL;
   // per-slot bias of rgb_net.1 (dir/time part), then the fused MLP
@@ -1566,9 +1629,10 @@ int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, 
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux; P.cbuf = cbuf;
-  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED;
+  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED || precision == STNERF_PREC_TC_3XF16_CF;
   P.single_last = precision == STNERF_PREC_TC_MIXED;
   P.raw = raw; P.rgb_out = rgb_out; P.sigma_out = sigma_out; P.lerp_force = 0;
+  P.lo_first = lo_first;
   if (fuse && fuse->on) {
     if (src.mode == SRC_EXPLICIT || src.S != 64 || !tc_can_fuse_coarse(fuse->n1, fuse->n2) || !fuse->t_fine) return STNERF_EINVAL;
     P.fuse = *fuse;
@@ -1577,13 +1641,14 @@ int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW&, 
 }
 
 int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW&, int precision, const int* lerp_flag_dev,
-                        int lerp_force, float* xyz_out, float* flow_out, int num_sms, cudaStream_t st) {
+                        int lerp_force, float* xyz_out, float* flow_out, int num_sms, cudaStream_t st, int lo_first) {
   if (!net.blob) return STNERF_ENOWEIGHTS;
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.src = src; P.wstream = (const uint8_t*)net.blob; P.aux = net.aux;
-  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED;      // the flow feeds positions: always split
+  P.exact = precision == STNERF_PREC_TC_3XF16 || precision == STNERF_PREC_TC_MIXED || precision == STNERF_PREC_TC_3XF16_CF;      // the flow feeds positions: always split
   P.xyz_out = xyz_out; P.flow_out = flow_out; P.lerp_flag = lerp_flag_dev; P.lerp_force = lerp_force;
+  P.lo_first = lo_first;
   return launch_tc<NET_MOTION>(P, num_sms, st);
 }
 

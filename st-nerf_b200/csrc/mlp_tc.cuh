@@ -48,10 +48,11 @@ int tc_selftest(float* max_err_host);   // one 128x128x64 UMMA vs a host referen
 int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host);   // accumulation probe (see mlp_tc.cu)
 int tc_selftest_pair(float* max_err_host);   // 256x256x64 through one cta_group::2 accumulator (two CTAs of a cluster)
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* cbuf, float* raw,
-                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse = nullptr);
+                       float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse = nullptr,
+                       int lo_first = 0);
 bool tc_can_fuse_coarse(int n1, int n2);     // sample counts the fused compositing warps are instantiated for
 int tc_launch_motionnet(const PointSrc& src, const TcNet& net, const MotionNetW& w32, int precision,
                         const int* lerp_flag_dev, int lerp_force, float* xyz_out, float* flow_out, int num_sms,
-                        cudaStream_t st);
+                        cudaStream_t st, int lo_first = 0);
 
 }  // namespace stnerf

@@ -11,8 +11,9 @@ MAX_LAYERS = 8
 MAX_N1 = 128
 MAX_S = 512
 
-PREC_FP32_SIMT, PREC_TC_3XF16, PREC_TC_F16, PREC_TC_MIXED = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32_SIMT, "exact": PREC_TC_3XF16, "tc3": PREC_TC_3XF16, "fast": PREC_TC_F16, "mixed": PREC_TC_MIXED}
+PREC_FP32_SIMT, PREC_TC_3XF16, PREC_TC_F16, PREC_TC_MIXED, PREC_TC_3XF16_CF = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "exact": PREC_TC_3XF16, "tc3": PREC_TC_3XF16, "fast": PREC_TC_F16, "mixed": PREC_TC_MIXED,
+              "exact_cf": PREC_TC_3XF16_CF}
 
 # STNERF_B200_LIB selects an alternative build of the same ABI (A/B experiments: __graft_entry__.build_variant)
 LIB_PATH = os.environ.get("STNERF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstnerf_b200.so")

@@ -93,6 +93,7 @@ def test_precision_enum_matches_python_map():
     from stnerf_b200 import _lib as L
     hdr = open(os.path.join(ROOT, "include", "stnerf.h")).read()
     enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"STNERF_PREC_(\w+)\s*=\s*(\d+)", hdr)}
-    assert enum == {"FP32_SIMT": 0, "TC_3XF16": 1, "TC_F16": 2, "TC_MIXED": 3}
+    assert enum == {"FP32_SIMT": 0, "TC_3XF16": 1, "TC_F16": 2, "TC_MIXED": 3, "TC_3XF16_CF": 4}
     assert L.PRECISIONS["fp32"] == enum["FP32_SIMT"] and L.PRECISIONS["exact"] == enum["TC_3XF16"]
     assert L.PRECISIONS["fast"] == enum["TC_F16"] and L.PRECISIONS["mixed"] == enum["TC_MIXED"]
+    assert L.PRECISIONS["exact_cf"] == enum["TC_3XF16_CF"]

@@ -175,22 +175,22 @@ def test_parity_at_scale_vs_reference(name):
     l = case["L"] + 1
     rays, jit, u = C.scale_inputs(case)
     report = {"case": name, "rays": int(rays.shape[0])}
-    for prec in ("exact", "mixed"):
+    for prec in ("exact", "exact_cf", "mixed"):
         model = build_case_model(case, precision=prec)
         flat = _render(model, rays, jit, u, case)
         for i in range(l):
             assert np.array_equal(flat["ray_mask.%d" % i], gold["ray_mask.%d" % i])
         err = _err(flat, gold, l)
-        out = np.nonzero(err > GATE)[0]
+        dd = np.abs(flat["fine_mixed.depth"] - gold["fine_mixed.depth"])[:, 0]
+        depth_off = dd > 2e-2 + 2e-3 * np.abs(gold["fine_mixed.depth"][:, 0])       # depth to the tolerance of test_gpu_render.py
+        out = np.nonzero((err > GATE) | depth_off)[0]                               # every such ray must be attributed below
         mse = float(((flat["fine_mixed.rgb"].astype(np.float64) - gold["fine_mixed.rgb"]) ** 2).mean())
-        rep = {"max_abs_err": float(err.max()), "rays_over_1e-3": int(out.size), "frac_over_1e-3": float(out.size / err.size),
+        rep = {"max_abs_err": float(err.max()), "rays_over_1e-3": int((err > GATE).sum()), "rays_over_gate_or_depth_tolerance": int(out.size),
+               "frac_over_1e-3": float((err > GATE).mean()),
                "median_err": float(np.median(err)), "p999_err": float(np.sort(err)[int(0.999 * err.size)]),
                "psnr_db": 99.0 if mse == 0 else float(10 * np.log10(1.0 / mse))}
         thresholds = case["thr"][0] != 0 or case["thr"][1] != 0
         assert out.size <= MAX_OUTLIER_FRACTION[thresholds] * err.size and rep["median_err"] < 5e-5, rep
-        ok = err <= GATE
-        dd = np.abs(flat["fine_mixed.depth"] - gold["fine_mixed.depth"])[ok]
-        assert (dd <= 2e-2 + 2e-3 * np.abs(gold["fine_mixed.depth"][ok])).all()
         if out.size:
             rep["attribution"] = attribute_outliers(case, model, rays, jit, u, out, flat, mixed=(prec == "mixed"))
         report[prec] = rep

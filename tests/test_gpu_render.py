@@ -48,6 +48,12 @@ def test_render_exact_tc_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", list(C.CASES))
+def test_render_exact_cf_tc_matches_reference(name):
+    """`exact_cf` (STNERF_PREC_TC_3XF16_CF): the correction products of the split go first in the coarse pass and the MotionNets."""
+    _check(name, "exact_cf", RGB_TOL)
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
 def test_render_mixed_tc_matches_reference(name):
     """`mixed`: 3-term split wherever the density depends on it, one fp16 pass on the colour-only layer rgb_net.1 -- same 1e-3
     gate on every ray, and the sampling (depths, masks) must be EXACTLY what `exact` produces (the colour branch cannot move a sample)."""
