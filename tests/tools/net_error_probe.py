@@ -47,7 +47,7 @@ for layer, fine, label in ((0, False, "bkgd coarse"), (1, False, "performer 1 co
              "reference fp32 (CPU)": {"sigma_rel_rms": float(((sig32.double() - sig64) / scale).pow(2).mean().sqrt()),
                                       "sigma_rel_max": float(((sig32.double() - sig64) / scale).abs().max()),
                                       "sigma_rel_mean_signed": float(((sig32.double() - sig64) / scale).mean())}}
-    for prec in ("fp32", "exact", "mixed"):
+    for prec in ("fp32", "exact", "exact_cf", "mixed"):
         model = build_case_model(dict(case, name=name), precision=prec)
         nat = model._ensure_native(torch.device("cuda", 0))
         rgb, sig = nat.spacenet(layer, fine, pos.cuda(), dirs.cuda(), tm.reshape(-1).cuda() if use_time else None)
