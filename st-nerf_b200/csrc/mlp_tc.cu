@@ -55,6 +55,9 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
+#ifndef PRODUCER_ELECT
+#define PRODUCER_ELECT 1              // 1 (default): the weight producer runs warp-wide with one elected issuing lane (0: single lane, A/B)
+#endif
 #ifndef MOTION_CTAS_PER_SM
 #define MOTION_CTAS_PER_SM 2          // resident CTAs per SM of the MotionNet instantiation (1 = single-CTA layout, kept for A/B)
 #endif
@@ -149,6 +152,82 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- warp-wide issue helpers: the MMA warp runs its loop on all 32 lanes, ONE elected lane issues ------------------------------
+// Under a plain `if (lane == 0)` ptxas cannot know that a single thread is active: it wraps every tcgen05 instruction in an
+// "elect an active lane, execute, retire it, repeat" loop and rebuilds both 64-bit descriptors per MMA.  The issuing thread is
+// latency-critical (a few extra instructions per MMA were measured at -4 %, profiles/r02_ab_lo_first.json).  Here the lane is
+// chosen by elect.sync inside the asm block (predicated instructions, no loop), a whole weight stage is issued per block and a
+// descriptor is a precomputed low word + a constant high word (32 bytes along K = +2 in the 16-byte address field).
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);        // SBO 512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
+// operands: %0 accumulator (TMEM), %1 A block 0, %2 A block 1, %3 weight stage, %4 instruction descriptor, %5 accumulate flag of the
+// first MMA, %6 barrier to commit to, %7 / %8 descriptor high words (A / B), %9 multicast mask
+#define STNERF_ISSUE_HEAD                                                                                                  \
+  "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 da, db0, db1;\n\t.reg .b32 t;\n\t"                                             \
+  "elect.sync _|pe, 0xffffffff;\n\t"                                                                                       \
+  "setp.ne.b32 pa, %5, 0;\n\t"                                                                                             \
+  "setp.eq.b32 pt, %5, %5;\n\t"                                                                                            \
+  "mov.b64 db0, {%3, %8};\n\t"                                                                                             \
+  "add.u32 t, %3, 2;\n\t"                                                                                                  \
+  "mov.b64 db1, {t, %8};\n\t"
+#define STNERF_ISSUE_A(AREG, PFIRST)                                                                                       \
+  "mov.b64 da, {" AREG ", %7};\n\t"                                                                                        \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db0, %4, " PFIRST ";\n\t"                                              \
+  "add.u32 t, " AREG ", 2;\n\t"                                                                                            \
+  "mov.b64 da, {t, %7};\n\t"                                                                                               \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db1, %4, pt;\n\t"
+#define STNERF_ISSUE_COMMIT_MC "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %9;\n\t}"
+#define STNERF_ISSUE_COMMIT_1 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
+#define STNERF_ISSUE_OPERANDS                                                                                              \
+  ::"r"(d_tmem), "r"(a0), "r"(a1), "r"(w), "r"(idesc), "r"(acc0), "r"(bar), "r"(DESC_HI_SW128), "r"(DESC_HI_SW64), "h"(mask) : "memory"
+
+// One weight stage [N x 32 k] (descriptor word `w`) times the 32-k slice of the A block at `a0` (two K=16 MMAs) and, with NA == 2,
+// of a second A block at `a1` as well (four MMAs), then tcgen05.commit on `bar` (MC: in both CTAs of the cluster).
+// acc0 == 0: the first MMA overwrites the accumulator.  Executed by the whole, converged warp.
+template <int NA, bool MC>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t w, uint32_t idesc, uint32_t acc0,
+                                            uint32_t bar) {
+  const uint16_t mask = 3;
+  if (NA == 1 && MC) asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_OPERANDS);
+  if (NA == 1 && !MC) asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
+  if (NA == 2 && MC)
+    asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_A("%2", "pt") STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_OPERANDS);
+  if (NA == 2 && !MC)
+    asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_A("%2", "pt") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
+}
+// tcgen05.commit by one elected lane of the converged warp ("every MMA issued so far has retired" -> one arrival on `bar`)
+__device__ __forceinline__ void commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+
+// Weight-stage load by one elected lane of the converged producer warp: announce `expect` bytes on `bar`, then the bulk copy
+// (MC: multicast into both CTAs of the cluster, completing bytes on the barrier at the same offset in each).
+template <bool MC>
+__device__ __forceinline__ void load_stage_elect(uint32_t dst, const void* src, uint32_t copy_bytes, uint32_t expect, uint32_t bar) {
+  const uint16_t mask = 3;
+  if (MC)
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %5;\n\t}" ::"r"(dst),
+        "l"(src), "r"(copy_bytes), "r"(bar), "r"(expect), "h"(mask)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+        "l"(src), "r"(copy_bytes), "r"(bar), "r"(expect)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -704,8 +783,42 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   // past the end, whose points are all invalid)
   auto in_range = [&](long long tile) { return (PAIR || WSHARE) ? ((tile & ~1LL) < n_tiles) : (tile < n_tiles); };
 
-  if (warp == 0) {
-    // =============================== weight producer ===============================
+  if (warp == 0 && !PAIR && PRODUCER_ELECT) {
+    // =============================== weight producer: the whole warp runs the loop, one elected lane issues ===============================
+    uint32_t cnt = 0;
+    for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
+      const uint8_t* src = P.wstream;
+      for (int l = 0; l < S::N_LAYERS; ++l) {
+        const int nsub = 2 * (S::act_chunks(l) + S::enc_chunks(l));
+        const uint32_t bytes = (uint32_t)S::n_out(l) * 64;
+        const bool sp = split(l);
+        // WSHARE: the whole stage lands in both CTAs (half from this CTA's copy, half from the peer's); this CTA issues its half to both
+        auto LOAD = [&](const uint8_t* stage) {
+          const uint32_t s = cnt % NST, n = cnt / NST;
+          mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
+          const uint32_t dst = sbase + S::ring_base + s * STAGE_STRIDE;
+          if (WSHARE) load_stage_elect<true>(dst + rank * (bytes / 2), stage + rank * (bytes / 2), bytes / 2, bytes, BAR(BAR_WFULL + s));
+          else load_stage_elect<false>(dst, stage, bytes, bytes, BAR(BAR_WFULL + s));
+          ++cnt;
+        };
+        // a layer of the stream = correction section [(hi, lo) per 32-k sub-chunk] + main section [hi per sub-chunk] (see the MMA warp)
+        const uint8_t* corr = src;
+        const uint8_t* mainp = src + (size_t)nsub * 2 * bytes;
+        if (!LOFIRST) {       // interleaved order: the (hi, lo) stages of the correction section serve all three products;
+          for (int sc = 0; sc < nsub; ++sc) {                      // single-pass layers never touch the lo stages
+            LOAD(corr + (size_t)(2 * sc) * bytes);
+            if (sp) LOAD(corr + (size_t)(2 * sc + 1) * bytes);
+          }
+        } else {
+          if (sp)
+            for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc) * bytes); LOAD(corr + (size_t)(2 * sc + 1) * bytes); }
+          for (int sc = 0; sc < nsub; ++sc) LOAD(mainp + (size_t)sc * bytes);
+        }
+        src = mainp + (size_t)nsub * bytes;
+      }
+    }
+  } else if (warp == 0) {
+    // =============================== weight producer (single lane: CTA-pair build, PRODUCER_ELECT=0) ===============================
     if (lane == 0) {
       uint32_t cnt = 0;
       for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
@@ -773,8 +886,84 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           }
         }
     }
+  } else if (warp == 1 && !PAIR) {
+    // =============================== MMA issuer: the whole warp runs the loop, one elected lane issues ===============================
+    uint32_t cnt = 0;            // weight stages consumed
+    uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
+    uint32_t a_par = 0;          // phase parity of a_ready[0..4], one bit each
+    for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
+      for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
+        const uint32_t b = g & 1;
+        mbar_wait(BAR(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);          // accumulator buffer drained (layer g-2)
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * S::d_stride;
+        const uint32_t idesc = idesc_n((uint32_t)S::n_out(l));
+        const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
+        const bool sp = split(l);
+        uint32_t acc = 0;        // the first MMA of the layer overwrites the accumulator
+        // descriptor words of the hi / lo halves of A chunk c (64 k); `wait`: first visit of the chunk in this layer
+        auto a_block = [&](int c, bool wait, uint32_t& a_hi, uint32_t& a_lo) {
+          uint32_t addr, lo_stride;
+          int bar_i = -1;
+          if (c < nact) {
+            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar_i = c;
+          } else {
+            const int e = c - nact;
+            addr = sbase + S::enc_base + e * ABLOCK; lo_stride = S::ENC_LO_STRIDE;
+            if (l == 0 && e == 0) bar_i = 4;                         // one arrival phase per tile covers the whole encoding
+          }
+          if (wait && bar_i >= 0) {
+            mbar_wait(BAR(BAR_AREADY + bar_i), (a_par >> bar_i) & 1u);
+            a_par ^= 1u << bar_i;
+            tc_fence_after();
+          }
+          a_hi = desc_lo(addr);
+          a_lo = desc_lo(addr + lo_stride);
+        };
+        // the next weight stage of the stream times the 32-k slice(s) of A at descriptor word(s) a0 (and a1)
+        auto stage2 = [&](uint32_t a0) {
+          const uint32_t s = cnt % NST, n = cnt / NST;
+          mbar_wait(BAR(BAR_WFULL + s), n & 1);
+          issue_stage<1, WSHARE>(d, a0, a0, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          acc = 1; ++cnt;
+        };
+        auto stage4 = [&](uint32_t a0, uint32_t a1) {
+          const uint32_t s = cnt % NST, n = cnt / NST;
+          mbar_wait(BAR(BAR_WFULL + s), n & 1);
+          issue_stage<2, WSHARE>(d, a0, a1, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          acc = 1; ++cnt;
+        };
+        if (!LOFIRST || !sp) {
+          // interleaved order (and single-pass layers): per 32-k sub-chunk Ahi*Whi and Alo*Whi off the hi stage, Ahi*Wlo off the lo stage
+          for (int c = 0; c < nch; ++c) {
+            uint32_t a_hi, a_lo;
+            a_block(c, true, a_hi, a_lo);
+#pragma unroll
+            for (uint32_t sub = 0; sub < 2; ++sub) {                  // 64 bytes along K = +4 in the address field
+              if (sp) { stage4(a_hi + 4 * sub, a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
+              else stage2(a_hi + 4 * sub);
+            }
+          }
+        } else {
+          // corrections first (see the file header): D = Alo*Whi + Ahi*Wlo over the whole K range, then D += Ahi*Whi off the main section
+          for (int c = 0; c < nch; ++c) {
+            uint32_t a_hi, a_lo;
+            a_block(c, true, a_hi, a_lo);
+#pragma unroll
+            for (uint32_t sub = 0; sub < 2; ++sub) { stage2(a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
+          }
+          for (int c = 0; c < nch; ++c) {
+            uint32_t a_hi, a_lo;
+            a_block(c, false, a_hi, a_lo);
+#pragma unroll
+            for (uint32_t sub = 0; sub < 2; ++sub) stage2(a_hi + 4 * sub);
+          }
+        }
+        commit_elect(BAR(BAR_DFULL + b));                              // accumulator of layer g complete
+      }
+    }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+    // =============================== MMA issuer (CTA-pair build: single lane, cta_group::2) ===============================
     if (lane == 0) {
       uint32_t cnt = 0;            // weight stages consumed
       uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
