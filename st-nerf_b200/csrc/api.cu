@@ -317,7 +317,7 @@ int stnerf_load_motionnet(stnerf_handle c, int layer, const float* blob, size_t 
 // ---- packed-weight image: every loaded network's device buffers, as they are, behind a small header ----
 namespace {
 constexpr char PACK_MAGIC[8] = {'S', 'T', 'N', 'B', '2', '0', '0', 'W'};
-constexpr uint32_t PACK_VERSION = 2;      // 2: weight stream = correction section + main section per layer
+constexpr uint32_t PACK_VERSION = 3;      // 2: weight stream = correction section + main section per layer; 3: skip layer's encoding chunk first
 struct PackHeader { char magic[8]; uint32_t version, n_layers, n_records, reserved; };
 struct PackRec { uint32_t kind, fine, layer, use_time; uint64_t simt_floats, stream_bytes, aux_floats, tail_floats; float scalars[4]; uint32_t pad[4]; };
 static size_t rec_payload(const PackRec& r) { return r.simt_floats * 4 + r.stream_bytes + r.aux_floats * 4 + r.tail_floats * 4; }

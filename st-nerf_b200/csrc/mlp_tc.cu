@@ -55,6 +55,9 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
+#ifndef SPACE_ENC_FIRST
+#define SPACE_ENC_FIRST 1             // 1 (default): the SpaceNet skip layer consumes its encoding chunk first (Sched::enc_first; 0: last, A/B)
+#endif
 #ifndef PRODUCER_ELECT
 #define PRODUCER_ELECT 1              // 1 (default): the weight producer runs warp-wide with one elected issuing lane (0: single lane, A/B)
 #endif
@@ -74,10 +77,11 @@ constexpr int SM_ENC = 8 * ABLOCK;           // 2 blocks: hi, lo (SpaceNet).  Mo
 constexpr int SM_RING = 10 * ABLOCK;
 constexpr int SM_MISC = SM_RING + NSTAGE * STAGE_BYTES;
 constexpr int MAX_STAGE = 8;                 // ring slots a kernel may use (CTA-pair mode: 8 half-size stages in the same 64 KB)
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 29, BAR_DEMPTY = 31,
-              BAR_RAWFULL = 33, BAR_RAWEMPTY = 34;                                                                // 35 barriers
-constexpr int MISC_TMEM = 280;
-constexpr int MISC_PART = 288;               // float[128][4]: head partial sums of column-half 1; with the coarse-pass fusion: the
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 33, BAR_DEMPTY = 35,
+              BAR_RAWFULL = 37, BAR_RAWEMPTY = 38;                                                                // 39 barriers
+constexpr int N_AREADY = 9, AREADY_ENC = 8;  // a_ready[2c + sub]: 32-k sub-chunk `sub` of activation chunk c written; [8]: the tile's encoding
+constexpr int MISC_TMEM = 312;
+constexpr int MISC_PART = 320;               // float[128][4]: head partial sums of column-half 1; with the coarse-pass fusion: the
                                              // tile's final (rgb logits, sigma) rows, read by the compositing warps
 constexpr int MISC_CDF = MISC_PART + 2048;   // fused compositing warps: cdf / depth scratch, 2 x 64 floats
 constexpr int SM_TOTAL = SM_MISC + MISC_CDF + 512;
@@ -241,6 +245,23 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
       : "r"(taddr)
       : "memory");
 }
+// two 16-column loads (the epilogue's two passes over a 64-column chunk) behind one wait
+__device__ __forceinline__ void tmem_ld16x2_issue(uint32_t taddr0, uint32_t taddr1, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr1)
+      : "memory");
+}
 // The registers are threaded through the wait so no consumer can be scheduled ahead of it.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -340,6 +361,9 @@ template <> struct Sched<NET_SPACE> {
   __host__ __device__ static constexpr int n_out(int l) { return l == 7 ? 128 : 256; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 4; }
   __host__ __device__ static constexpr int enc_chunks(int l) { return (l == 0 || l == 4) ? 1 : 0; }
+  // the skip layer consumes its encoding chunk FIRST: those MMAs do not depend on the previous layer's epilogue, so they run
+  // while the tensor pipe would otherwise wait for the first activation sub-chunk (the weight stream is packed in the same order)
+  __host__ __device__ static constexpr bool enc_first(int l) { return SPACE_ENC_FIRST != 0 && l == 4; }
   // CTA shape and shared/tensor-memory map: one CTA per SM, the whole 227 KB and all 512 TMEM columns
   static constexpr int N_THREADS = NTHREADS, EPI_W0 = EPI_WARP0, CTAS_PER_SM = 1;
   static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
@@ -354,6 +378,7 @@ template <> struct Sched<NET_MOTION> {
   __host__ __device__ static constexpr int n_out(int) { return 128; }
   __host__ __device__ static constexpr int act_chunks(int l) { return l == 0 ? 0 : 2; }
   __host__ __device__ static constexpr int enc_chunks(int l) { return l == 0 ? 2 : 0; }
+  __host__ __device__ static constexpr bool enc_first(int) { return false; }
 #if MOTION_CTAS_PER_SM == 2
   // Two CTAs per SM.  A MotionNet tile is a serial chain (5 layers of N=128: two 64-column chunks per layer leave nothing to
   // pipeline inside a tile), so the tensor pipe idles while the epilogue warps work and vice versa; a second resident CTA
@@ -601,53 +626,69 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
                                                   , EpiTiming& tm
 #endif
 ) {
+  // The thread owns columns [hh*16, hh*16+16) of BOTH 32-column halves of the chunk: after its first 16 columns the first 32-k
+  // sub-chunk of the next layer's A operand is complete (all eight warps arrive on ready_bar), after the second 16 the other one
+  // (ready_bar + 8).  The next layer's MMAs start after HALF a chunk's epilogue -- the per-layer bubble the tensor pipe waits out.
   uint32_t acc[32];
-  const int col0 = j * 64 + hh * 32;
+  const int colA = j * 64 + hh * 16, colB = colA + 32;
   TSTAMP(t0);
-  tmem_ld32_issue(dcol + (uint32_t)col0, acc);
+  tmem_ld16x2_issue(dcol + (uint32_t)colA, dcol + (uint32_t)colB, acc);
   float4 bv[8], wv[8];
   {
-    const float4* bp = reinterpret_cast<const float4*>(bias + col0);      // L1-resident; overlaps the TMEM load
+    const float4* bpA = reinterpret_cast<const float4*>(bias + colA);     // L1-resident; overlaps the TMEM load
+    const float4* bpB = reinterpret_cast<const float4*>(bias + colB);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+    for (int i = 0; i < 4; ++i) { bv[i] = __ldg(bpA + i); bv[4 + i] = __ldg(bpB + i); }
     if (SIGMA) {
-      const float4* wp = reinterpret_cast<const float4*>(wdot + col0);
+      const float4* wpA = reinterpret_cast<const float4*>(wdot + colA);
+      const float4* wpB = reinterpret_cast<const float4*>(wdot + colB);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) wv[i] = __ldg(wp + i);
+      for (int i = 0; i < 4; ++i) { wv[i] = __ldg(wpA + i); wv[4 + i] = __ldg(wpB + i); }
     }
   }
   tmem_ld_wait(acc);
   TSTAMP(t1);
+#ifdef STNERF_TIMING
+  long long t2 = t1, t3 = t1;
+#endif
 #pragma unroll
-  for (int gq = 0; gq < 4; ++gq) {                     // 8 columns -> one 16-byte chunk
-    uint32_t hp[4], lp[4];
+  for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = gq * 8 + e * 2;
-      const float4 bb = bv[c >> 2];
-      const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
-      const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
-      const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
-      if (SIGMA) {
-        const float4 ww = wv[c >> 2];
-        dot = fmaf(v0, (c & 2) ? ww.z : ww.x, dot);
-        dot = fmaf(v1, (c & 2) ? ww.w : ww.y, dot);
+    for (int gh = 0; gh < 2; ++gh) {                   // 8 columns -> one 16-byte chunk
+      const int gq = pass * 2 + gh;                    // position in acc / bv / wv
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = gq * 8 + e * 2;
+        const float4 bb = bv[c >> 2];
+        const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
+        const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
+        const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
+        if (SIGMA) {
+          const float4 ww = wv[c >> 2];
+          dot = fmaf(v0, (c & 2) ? ww.z : ww.x, dot);
+          dot = fmaf(v1, (c & 2) ? ww.w : ww.y, dot);
+        }
+        hp[e] = pack_f16x2(v0, v1);
+        if (exact) {
+          const float2 hf = unpack_f16x2(hp[e]);
+          lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
+        }
       }
-      hp[e] = pack_f16x2(v0, v1);
-      if (exact) {
-        const float2 hf = unpack_f16x2(hp[e]);
-        lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
-      }
+      const uint32_t off = sw128_offset(row, pass * 32 + hh * 16 + gh * 8);
+      *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      if (exact) *reinterpret_cast<uint4*>(blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
-    const uint32_t off = sw128_offset(row, hh * 32 + gq * 8);
-    *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-    if (exact) *reinterpret_cast<uint4*>(blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+#ifdef STNERF_TIMING
+    if (pass == 1) t2 = clock64();
+#endif
+    fence_proxy_async();
+    __syncwarp();
+#ifdef STNERF_TIMING
+    if (pass == 1) t3 = clock64();
+#endif
+    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar + 8u * pass); else mbar_arrive(ready_bar + 8u * pass); }
   }
-  TSTAMP(t2);
-  fence_proxy_async();
-  __syncwarp();
-  TSTAMP(t3);
-  if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar); else mbar_arrive(ready_bar); }
 #ifdef STNERF_TIMING
   const long long t4 = clock64();
   tm.ld += t1 - t0; tm.math += t2 - t1; tm.fence += t3 - t2; tm.arrive += t4 - t3; tm.n += 1;
@@ -765,7 +806,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   static_assert(NST <= MAX_STAGE, "barrier slots");
   if (tid == 0) {
     for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), WSHARE ? 2 : 1); mbar_init(BAR(BAR_WPEER + i), 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(BAR(BAR_AREADY + i), N_ARRIVE);
+    for (int i = 0; i < N_AREADY; ++i) mbar_init(BAR(BAR_AREADY + i), N_ARRIVE);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_DFULL + i), 1); mbar_init(BAR(BAR_DEMPTY + i), N_ARRIVE); }
     mbar_init(BAR(BAR_RAWFULL), 4);          // the four epilogue warps that own the tile's final rows
     mbar_init(BAR(BAR_RAWEMPTY), 2);         // the two compositing warps
@@ -890,7 +931,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     // =============================== MMA issuer: the whole warp runs the loop, one elected lane issues ===============================
     uint32_t cnt = 0;            // weight stages consumed
     uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
-    uint32_t a_par = 0;          // phase parity of a_ready[0..4], one bit each
+    uint32_t a_par = 0;          // phase parity of a_ready[0..8], one bit each
     for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
       for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
         const uint32_t b = g & 1;
@@ -901,24 +942,27 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
         const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
         const bool sp = split(l);
         uint32_t acc = 0;        // the first MMA of the layer overwrites the accumulator
-        // descriptor words of the hi / lo halves of A chunk c (64 k); `wait`: first visit of the chunk in this layer
-        auto a_block = [&](int c, bool wait, uint32_t& a_hi, uint32_t& a_lo) {
+        // descriptor words of the hi / lo halves of A chunk c (64 k), and the a_ready barrier of its first 32-k sub-chunk (-1: none;
+        // the encoding has ONE arrival phase per tile, waited for at its first use: layer 0, chunk 0, sub-chunk 0)
+        auto a_block = [&](int c, uint32_t& a_hi, uint32_t& a_lo, int& bar0, int& bar1) {
           uint32_t addr, lo_stride;
-          int bar_i = -1;
           if (c < nact) {
-            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar_i = c;
+            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar0 = 2 * c; bar1 = 2 * c + 1;
           } else {
             const int e = c - nact;
             addr = sbase + S::enc_base + e * ABLOCK; lo_stride = S::ENC_LO_STRIDE;
-            if (l == 0 && e == 0) bar_i = 4;                         // one arrival phase per tile covers the whole encoding
-          }
-          if (wait && bar_i >= 0) {
-            mbar_wait(BAR(BAR_AREADY + bar_i), (a_par >> bar_i) & 1u);
-            a_par ^= 1u << bar_i;
-            tc_fence_after();
+            bar0 = (l == 0 && e == 0) ? AREADY_ENC : -1; bar1 = -1;
           }
           a_hi = desc_lo(addr);
           a_lo = desc_lo(addr + lo_stride);
+        };
+        // position c of the layer's K order -> chunk id (activation chunks 0..nact-1, then the encoding chunks)
+        auto chunk_at = [&](int c) { return (S::enc_first(l) && nact > 0 && nch > nact) ? (c == 0 ? nact : c - 1) : c; };
+        auto a_wait = [&](int bar_i) {           // the epilogue (or the encoder) has written this sub-chunk of the A operand
+          if (bar_i < 0) return;
+          mbar_wait(BAR(BAR_AREADY + bar_i), (a_par >> bar_i) & 1u);
+          a_par ^= 1u << bar_i;
+          tc_fence_after();
         };
         // the next weight stage of the stream times the 32-k slice(s) of A at descriptor word(s) a0 (and a1)
         auto stage2 = [&](uint32_t a0) {
@@ -937,9 +981,11 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           // interleaved order (and single-pass layers): per 32-k sub-chunk Ahi*Whi and Alo*Whi off the hi stage, Ahi*Wlo off the lo stage
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
-            a_block(c, true, a_hi, a_lo);
+            int bar[2];
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) {                  // 64 bytes along K = +4 in the address field
+              a_wait(bar[sub]);
               if (sp) { stage4(a_hi + 4 * sub, a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
               else stage2(a_hi + 4 * sub);
             }
@@ -948,13 +994,15 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           // corrections first (see the file header): D = Alo*Whi + Ahi*Wlo over the whole K range, then D += Ahi*Whi off the main section
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
-            a_block(c, true, a_hi, a_lo);
+            int bar[2];
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
 #pragma unroll
-            for (uint32_t sub = 0; sub < 2; ++sub) { stage2(a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
+            for (uint32_t sub = 0; sub < 2; ++sub) { a_wait(bar[sub]); stage2(a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
           }
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
-            a_block(c, false, a_hi, a_lo);
+            int bar[2];
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) stage2(a_hi + 4 * sub);
           }
@@ -967,7 +1015,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     if (lane == 0) {
       uint32_t cnt = 0;            // weight stages consumed
       uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
-      uint32_t a_uses[5] = {0, 0, 0, 0, 0};
+      uint32_t a_uses[N_AREADY] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       auto WAIT = [&](uint32_t bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
       for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
         for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
@@ -979,20 +1027,23 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
           if (!LOFIRST) {
             // interleaved order: per 32-k sub-chunk, Ahi*Whi and Alo*Whi off the hi stage, Ahi*Wlo off the lo stage
-            for (int c = 0; c < nch; ++c) {
+            for (int cpos = 0; cpos < nch; ++cpos) {
+              const int c = (S::enc_first(l) && nact > 0 && nch > nact) ? (cpos == 0 ? nact : cpos - 1) : cpos;
               uint32_t a_hi, a_lo;
               if (c < nact) {
                 a_hi = sbase + S::act_base + c * ABLOCK;
                 a_lo = a_hi + S::LO_STRIDE;
-                WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1);
-                ++a_uses[c];
+                WAIT(BAR(BAR_AREADY + 2 * c), a_uses[2 * c] & 1);          // both 32-k sub-chunks of the chunk
+                ++a_uses[2 * c];
+                WAIT(BAR(BAR_AREADY + 2 * c + 1), a_uses[2 * c + 1] & 1);
+                ++a_uses[2 * c + 1];
               } else {
                 const int e = c - nact;
                 a_hi = sbase + S::enc_base + e * ABLOCK;
                 a_lo = a_hi + S::ENC_LO_STRIDE;
                 if (l == 0 && e == 0) {                              // one arrival phase per tile covers the whole encoding
-                  WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
-                  ++a_uses[4];
+                  WAIT(BAR(BAR_AREADY + AREADY_ENC), a_uses[AREADY_ENC] & 1);
+                  ++a_uses[AREADY_ENC];
                 }
               }
               tc_fence_after();
@@ -1011,7 +1062,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
                     else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
                   };
 #pragma unroll
-                  for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (c == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
+                  for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (cpos == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
                   if (term == 0 && split(l)) {
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
@@ -1034,14 +1085,17 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               if (c < nact) {
                 a_hi = sbase + S::act_base + c * ABLOCK;
                 a_lo = a_hi + S::LO_STRIDE;
-                if (wait) { WAIT(BAR(BAR_AREADY + c), a_uses[c] & 1); ++a_uses[c]; }
+                if (wait) {
+                  WAIT(BAR(BAR_AREADY + 2 * c), a_uses[2 * c] & 1); ++a_uses[2 * c];
+                  WAIT(BAR(BAR_AREADY + 2 * c + 1), a_uses[2 * c + 1] & 1); ++a_uses[2 * c + 1];
+                }
               } else {
                 const int e = c - nact;
                 a_hi = sbase + S::enc_base + e * ABLOCK;
                 a_lo = a_hi + S::ENC_LO_STRIDE;
                 if (wait && l == 0 && e == 0) {                      // one arrival phase per tile covers the whole encoding
-                  WAIT(BAR(BAR_AREADY + 4), a_uses[4] & 1);
-                  ++a_uses[4];
+                  WAIT(BAR(BAR_AREADY + AREADY_ENC), a_uses[AREADY_ENC] & 1);
+                  ++a_uses[AREADY_ENC];
                 }
               }
               if (wait) tc_fence_after();
@@ -1069,7 +1123,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             if (sp) {
               for (int c = 0; c < nch; ++c) {
                 uint32_t a_hi, a_lo;
-                chunk(c, true, a_hi, a_lo);
+                chunk((S::enc_first(l) && nact > 0 && nch > nact) ? (c == 0 ? nact : c - 1) : c, true, a_hi, a_lo);
                 for (int sub = 0; sub < 2; ++sub) {                  // correction pass: D = Alo*Whi + Ahi*Wlo
                   STAGE(a_lo + (uint32_t)sub * 64);                  // hi weight stage
                   STAGE(a_hi + (uint32_t)sub * 64);                  // lo weight stage
@@ -1078,7 +1132,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             }
             for (int c = 0; c < nch; ++c) {                          // main pass: D += Ahi*Whi
               uint32_t a_hi, a_lo;
-              chunk(c, !sp, a_hi, a_lo);
+              chunk((S::enc_first(l) && nact > 0 && nch > nact) ? (c == 0 ? nact : c - 1) : c, !sp, a_hi, a_lo);
               for (int sub = 0; sub < 2; ++sub) STAGE(a_hi + (uint32_t)sub * 64);
             }
           }
@@ -1130,7 +1184,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       if (NET == NET_MOTION) encode_piece<NET, 2>(smem, cur, row, hh, exact, lerp, carry);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ARRIVE(BAR_AREADY + 4);
+      if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
     }
     uint32_t tile_no = 0;                       // tiles this CTA has finished (phase of the fused compositing hand-off)
     for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x, ++tile_no) {
@@ -1155,7 +1209,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           if (NET == NET_SPACE && l == 6) {
             for (int j = 0; j < nchunk; ++j)
               sig_dot = epi_hidden_chunk<true, PAIR>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
-                                                     S::LO_STRIDE, split(l + 1), lane, LBAR(BAR_AREADY + j), sig_dot
+                                                     S::LO_STRIDE, split(l + 1), lane, LBAR(BAR_AREADY + 2 * j), sig_dot
 #ifdef STNERF_TIMING
                                                , tm
 #endif
@@ -1163,7 +1217,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           } else {
             for (int j = 0; j < nchunk; ++j)
               epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, split(l + 1),
-                                            lane, LBAR(BAR_AREADY + j), 0.f
+                                            lane, LBAR(BAR_AREADY + 2 * j), 0.f
 #ifdef STNERF_TIMING
                                       , tm
 #endif
@@ -1188,7 +1242,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               if (l == L_P0 + (NET == NET_SPACE ? 1 : 2)) {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) ARRIVE(BAR_AREADY + 4);
+                if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
               }
             }
 #ifdef STNERF_TIMING
@@ -1258,7 +1312,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             if (NET == NET_MOTION) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) ARRIVE(BAR_AREADY + 4);
+            if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
           }
           // combine the two column halves through shared memory.  With the coarse-pass fusion the tile's FINAL rows go to
           // `s_part` for the compositing warps, so the half sums travel through the first activation block instead: every
@@ -1632,9 +1686,11 @@ int tc_pack_spacenet(TcNet& net, const float* p, bool use_time) {
   for (int i = 0; i < 7; ++i) {
     LayerSpec L;
     L.W = p; L.N = HID; L.K_total = Ks[i];
+    const bool enc_first = Sched<NET_SPACE>::enc_first(i);
+    if (i == 4 && enc_first) L.chunks.push_back(enc_perm_space(HID));   // cat[x, PE(pos)] (spacenet.py:137): consumed first
     if (i != 0) for (int k = 0; k < HID; k += 64) L.chunks.push_back(iota_chunk(k, HID));
     if (i == 0) L.chunks.push_back(enc_perm_space(0));
-    if (i == 4) L.chunks.push_back(enc_perm_space(HID));            // cat[x, PE(pos)] (spacenet.py:137)
+    if (i == 4 && !enc_first) L.chunks.push_back(enc_perm_space(HID));
     layers.push_back(L);
     p += (size_t)HID * Ks[i];
     memcpy(aux.data() + AUX_BIAS + i * 256, p, HID * sizeof(float));
