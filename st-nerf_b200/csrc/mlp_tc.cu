@@ -55,9 +55,6 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
-#ifndef SPACE_ACOLLECT
-#define SPACE_ACOLLECT 0              // 1: split layers take both stages of a sub-chunk at once and reuse the A tile through the collector (A/B)
-#endif
 #ifndef SPACE_ENC_FIRST
 #define SPACE_ENC_FIRST 1             // 1 (default): the SpaceNet skip layer consumes its encoding chunk first (Sched::enc_first; 0: last, A/B)
 #endif
@@ -204,40 +201,6 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a0, uint32
     asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_A("%2", "pt") STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_OPERANDS);
   if (NA == 2 && !MC)
     asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_A("%2", "pt") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
-}
-// A/B (SPACE_ACOLLECT=1): both weight stages (hi at `wh`, lo at `wl`) of a 32-k sub-chunk at once, so that the two products that
-// share an A tile are adjacent -- Ahi*Whi (collector::a::fill) then Ahi*Wlo (collector::a::lastuse): the second MMA takes the A tile
-// from the tensor core's collector instead of shared memory (A read 4 times instead of 6 per sub-chunk).  Commits on both ring slots.
-template <bool MC>
-__device__ __forceinline__ void issue_pair_collect(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t wh, uint32_t wl, uint32_t idesc,
-                                                   uint32_t acc0, uint32_t bar0, uint32_t bar1) {
-  const uint16_t mask = 3;
-#define STNERF_PAIR_BODY                                                                                                   \
-  "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 dah0, dah1, dal0, dal1, bh0, bh1, bl0, bl1;\n\t.reg .b32 t;\n\t"               \
-  "elect.sync _|pe, 0xffffffff;\n\t"                                                                                       \
-  "setp.ne.b32 pa, %6, 0;\n\t"                                                                                             \
-  "setp.eq.b32 pt, %6, %6;\n\t"                                                                                            \
-  "mov.b64 dah0, {%1, %9};\n\t add.u32 t, %1, 2;\n\t mov.b64 dah1, {t, %9};\n\t"                                           \
-  "mov.b64 dal0, {%2, %9};\n\t add.u32 t, %2, 2;\n\t mov.b64 dal1, {t, %9};\n\t"                                           \
-  "mov.b64 bh0, {%3, %10};\n\t add.u32 t, %3, 2;\n\t mov.b64 bh1, {t, %10};\n\t"                                           \
-  "mov.b64 bl0, {%4, %10};\n\t add.u32 t, %4, 2;\n\t mov.b64 bl1, {t, %10};\n\t"                                           \
-  "@pe tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], dah0, bh0, %5, pa;\n\t"                                 \
-  "@pe tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], dah0, bl0, %5, pt;\n\t"                              \
-  "@pe tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], dah1, bh1, %5, pt;\n\t"                                 \
-  "@pe tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], dah1, bl1, %5, pt;\n\t"                              \
-  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], dal0, bh0, %5, pt;\n\t"                                                    \
-  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], dal1, bh1, %5, pt;\n\t"
-#define STNERF_PAIR_OPERANDS                                                                                               \
-  ::"r"(d_tmem), "r"(ah), "r"(al), "r"(wh), "r"(wl), "r"(idesc), "r"(acc0), "r"(bar0), "r"(bar1), "r"(DESC_HI_SW128),      \
-      "r"(DESC_HI_SW64), "h"(mask) : "memory"
-  if (MC)
-    asm volatile(STNERF_PAIR_BODY
-                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %11;\n\t"
-                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t}" STNERF_PAIR_OPERANDS);
-  else
-    asm volatile(STNERF_PAIR_BODY
-                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}" STNERF_PAIR_OPERANDS);
 }
 // tcgen05.commit by one elected lane of the converged warp ("every MMA issued so far has retired" -> one arrival on `bar`)
 __device__ __forceinline__ void commit_elect(uint32_t bar) {
@@ -1023,15 +986,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) {                  // 64 bytes along K = +4 in the address field
               a_wait(bar[sub]);
-              if (sp && SPACE_ACOLLECT) {
-                const uint32_t s0 = cnt % NST, n0 = cnt / NST, s1 = (cnt + 1) % NST, n1 = (cnt + 1) / NST;
-                mbar_wait(BAR(BAR_WFULL + s0), n0 & 1);
-                mbar_wait(BAR(BAR_WFULL + s1), n1 & 1);
-                issue_pair_collect<WSHARE>(d, a_hi + 4 * sub, a_lo + 4 * sub, desc_lo(sbase + S::ring_base + s0 * STAGE_STRIDE),
-                                           desc_lo(sbase + S::ring_base + s1 * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s0),
-                                           BAR(BAR_WEMPTY + s1));
-                acc = 1; cnt += 2;
-              } else if (sp) { stage4(a_hi + 4 * sub, a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
+              if (sp) { stage4(a_hi + 4 * sub, a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
               else stage2(a_hi + 4 * sub);
             }
           }
