@@ -55,9 +55,6 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
-#ifndef SPACE_DEFER_HEAD
-#define SPACE_DEFER_HEAD 1            // 1 (default): second half of a tile's fp32 head deferred behind the next tile's first chunks (0: A/B)
-#endif
 #ifndef SPACE_ENC_FIRST
 #define SPACE_ENC_FIRST 1             // 1 (default): the SpaceNet skip layer consumes its encoding chunk first (Sched::enc_first; 0: last, A/B)
 #endif
@@ -1189,102 +1186,6 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
       __syncwarp();
       if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
     }
-    // ---- the 3-wide fp32 head of the last layer (see the `last` branch of the layer loop) ----
-    constexpr bool DEFER_HEAD = (NET == NET_SPACE) && !PAIR && (SPACE_DEFER_HEAD != 0);
-    bool pend_on = false;                       // a tile's head is half done (deferred behind the next tile's first chunks)
-    Pt pend_pt = cur;
-    long long pend_tile = 0;
-    uint32_t pend_tile_no = 0;
-    float pend_sig = 0.f, pend_dot[3] = {0.f, 0.f, 0.f};
-    // dot3 += W_out[:, col0 .. col0+32) . relu(acc + bias)
-    auto head_half = [&](const uint32_t (&acc)[32], const float4 (&bb4)[8], int col0, float (&dot3)[3]) {
-      float v[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float4 bb = bb4[c >> 2];
-        const float bc = (c & 3) == 0 ? bb.x : (c & 3) == 1 ? bb.y : (c & 3) == 2 ? bb.z : bb.w;
-        v[c] = fmaxf(__uint_as_float(acc[c]) + bc, 0.f);
-      }
-#pragma unroll
-      for (int o = 0; o < 3; ++o) {
-        const float4* wp = reinterpret_cast<const float4*>(P.aux + AUX_WOUT + o * 128 + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 ww = __ldg(wp + i);
-          dot3[o] = fmaf(v[4 * i], ww.x, dot3[o]);
-          dot3[o] = fmaf(v[4 * i + 1], ww.y, dot3[o]);
-          dot3[o] = fmaf(v[4 * i + 2], ww.z, dot3[o]);
-          dot3[o] = fmaf(v[4 * i + 3], ww.w, dot3[o]);
-        }
-      }
-    };
-    // combine the two column halves of a tile's head through shared memory and write the tile's outputs
-    auto head_finish = [&](const float (&dot3)[3], float sig_dot, const Pt& pt, long long tile_of, uint32_t tile_no_of) {
-      // With the coarse-pass fusion the tile's FINAL rows go to `s_part` for the compositing warps, so the half sums travel
-      // through the first 2 KB of activation chunk 2 instead: dead until the layer-0 epilogue of the next tile reaches that chunk
-      // (this code runs before it: either after the tile's last MMAs, or -- deferred -- after the first two chunks of the next
-      // tile's layer-0 epilogue, whose writes stay inside chunks 0 and 1).
-      const bool fused = (NET == NET_SPACE) && !PAIR && P.fuse.on;
-      float* s_half = fused ? reinterpret_cast<float*>(smem + S::act_base + (DEFER_HEAD ? 2 * ABLOCK : 0)) : s_part;
-      if (hh == 1) {
-        s_half[row * 4 + 0] = dot3[0]; s_half[row * 4 + 1] = dot3[1]; s_half[row * 4 + 2] = dot3[2];
-        s_half[row * 4 + 3] = sig_dot;
-      }
-      epi_bar_sync();
-      if (fused && hh == 0) {
-        // the compositing warps must be done with the previous tile's rows (they have had a whole tile period)
-        if (tile_no_of > 0) mbar_wait(BAR(BAR_RAWEMPTY), (tile_no_of - 1) & 1);
-        const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
-        const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
-        const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
-        const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
-        reinterpret_cast<float4*>(s_part)[row] = make_float4(o0, o1, o2, sg);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(BAR_RAWFULL));
-      }
-      if (hh == 0 && pt.out_index >= 0) {
-        const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
-        const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
-        const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
-        const int oi = pt.out_index;
-        if (NET == NET_SPACE) {
-          const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
-          if (P.raw) reinterpret_cast<float4*>(P.raw)[oi] = make_float4(o0, o1, o2, sg);
-          if (P.rgb_out) { P.rgb_out[3 * (size_t)oi] = o0; P.rgb_out[3 * (size_t)oi + 1] = o1; P.rgb_out[3 * (size_t)oi + 2] = o2; }
-          if (P.sigma_out) P.sigma_out[oi] = sg;
-        } else {
-          const long long p = tile_of * TILE_M + row;          // compact point index
-          if (P.flow_out) { P.flow_out[3 * p] = o0; P.flow_out[3 * p + 1] = o1; P.flow_out[3 * p + 2] = o2; }
-          if (P.xyz_out) {                                  // layered_rfrender.py:356 / :510
-            P.xyz_out[3 * p] = __fadd_rn(pt.x, o0);
-            P.xyz_out[3 * p + 1] = __fadd_rn(pt.y, o1);
-            P.xyz_out[3 * p + 2] = __fadd_rn(pt.z, o2);
-          }
-        }
-      }
-      epi_bar_sync();       // the half sums are rewritten by the next tile
-    };
-    // second half of a deferred head: the stashed accumulator columns come back from activation chunk 3 (own bytes, see above)
-    auto head_resume = [&]() {
-      uint32_t acc1[32];
-#pragma unroll
-      for (int gq = 0; gq < 4; ++gq) {
-        const uint32_t off = sw128_offset(row, (gq >> 1) * 32 + hh * 16 + (gq & 1) * 8);
-        const uint8_t* blk = smem + S::act_base + 3 * ABLOCK;
-        const uint4 lo4 = *reinterpret_cast<const uint4*>(blk + off);
-        const uint4 hi4 = *reinterpret_cast<const uint4*>(blk + S::LO_STRIDE + off);
-        acc1[8 * gq] = lo4.x; acc1[8 * gq + 1] = lo4.y; acc1[8 * gq + 2] = lo4.z; acc1[8 * gq + 3] = lo4.w;
-        acc1[8 * gq + 4] = hi4.x; acc1[8 * gq + 5] = hi4.y; acc1[8 * gq + 6] = hi4.z; acc1[8 * gq + 7] = hi4.w;
-      }
-      float4 bb4[8];
-      const float4* bp = reinterpret_cast<const float4*>(P.cbuf + (size_t)pend_pt.cidx * 128 + 64 + hh * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) bb4[i] = __ldg(bp + i);
-      float dot3[3] = {pend_dot[0], pend_dot[1], pend_dot[2]};
-      head_half(acc1, bb4, 64 + hh * 32, dot3);
-      head_finish(dot3, pend_sig, pend_pt, pend_tile, pend_tile_no);
-      pend_on = false;
-    };
     uint32_t tile_no = 0;                       // tiles this CTA has finished (phase of the fused compositing hand-off)
     for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x, ++tile_no) {
       const long long nt = tile + gridDim.x;
@@ -1314,15 +1215,13 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
 #endif
               );
           } else {
-            for (int j = 0; j < nchunk; ++j) {
+            for (int j = 0; j < nchunk; ++j)
               epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, split(l + 1),
                                             lane, LBAR(BAR_AREADY + 2 * j), 0.f
 #ifdef STNERF_TIMING
                                       , tm
 #endif
               );
-              if (DEFER_HEAD && j == 1 && pend_on) head_resume();      // the previous tile's head (only ever pending in layer 0)
-            }
           }
           tc_fence_before();
           __syncwarp();
@@ -1365,77 +1264,99 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           tc_fence_after();
           TSTAMP(tl1);
           float dot3[3] = {0.f, 0.f, 0.f};
-          if (!DEFER_HEAD) {
-            // one 32-column half at a time (the MotionNet instantiation has 96 registers per thread)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint32_t acc[32];
-              const int col0 = j * 64 + hh * 32;
-              tmem_ld32_issue(dcol + (uint32_t)col0, acc);
-              float4 bn4[8];
-              if (j == 0) {
-                const float4* bp = reinterpret_cast<const float4*>(brow + 64 + hh * 32);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bn4[i] = __ldg(bp + i);
-              }
-              tmem_ld_wait(acc);
-              head_half(acc, bb4, col0, dot3);
-              if (j == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bb4[i] = bn4[i];
-              }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ARRIVE(BAR_DEMPTY + b);
-            if (S::ENC_ALIASES_ACT && have_next) {
-              // The last layer's MMAs have retired (d_full above), so nothing reads the activation blocks any more: the next
-              // tile's encoding goes into them now, and its layer 0 runs while this tile's head is combined and written out.
-              zero_motion_pads();
-              encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
-              encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
-              if (NET == NET_MOTION) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
-            }
-            head_finish(dot3, sig_dot, cur, tile, tile_no);
-          } else {
-            // Deferred head (SpaceNet).  Both 32-column halves of this thread's 64 columns leave tensor memory at once, so the
-            // accumulator buffer is free for the next tile's layer 1 before any of the head arithmetic; only the first half is
-            // combined now.  The second half waits in the bytes of activation chunk 3 that this very thread overwrites in the next
-            // tile's layer-0 epilogue (all MMAs of this tile have retired, the next tile's layer 0 reads the encoding buffer only)
-            // and is finished after the first two chunks of that epilogue (head_resume) -- the next tile's layer 1 starts ~2 k
-            // cycles earlier instead of waiting behind the whole head.  The CTA's last tile is finished on the spot.
-            uint32_t acc0[32], acc1[32];
-            tmem_ld32_issue(dcol + (uint32_t)(hh * 32), acc0);
-            tmem_ld32_issue(dcol + (uint32_t)(64 + hh * 32), acc1);
-            tmem_ld_wait(acc0);
-            tmem_ld_wait(acc1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ARRIVE(BAR_DEMPTY + b);
-            if (have_next) {
-#pragma unroll
-              for (int gq = 0; gq < 4; ++gq) {
-                const uint32_t off = sw128_offset(row, (gq >> 1) * 32 + hh * 16 + (gq & 1) * 8);
-                uint8_t* blk = smem + S::act_base + 3 * ABLOCK;
-                *reinterpret_cast<uint4*>(blk + off) = make_uint4(acc1[8 * gq], acc1[8 * gq + 1], acc1[8 * gq + 2], acc1[8 * gq + 3]);
-                *reinterpret_cast<uint4*>(blk + S::LO_STRIDE + off) =
-                    make_uint4(acc1[8 * gq + 4], acc1[8 * gq + 5], acc1[8 * gq + 6], acc1[8 * gq + 7]);
-              }
-              head_half(acc0, bb4, hh * 32, dot3);
-              pend_on = true; pend_pt = cur; pend_tile = tile; pend_tile_no = tile_no; pend_sig = sig_dot;
-              pend_dot[0] = dot3[0]; pend_dot[1] = dot3[1]; pend_dot[2] = dot3[2];
-            } else {
-              head_half(acc0, bb4, hh * 32, dot3);
+          for (int j = 0; j < 2; ++j) {
+            uint32_t acc[32];
+            const int col0 = j * 64 + hh * 32;
+            tmem_ld32_issue(dcol + (uint32_t)col0, acc);
+            float4 bn4[8];
+            if (j == 0) {
               const float4* bp = reinterpret_cast<const float4*>(brow + 64 + hh * 32);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) bb4[i] = __ldg(bp + i);
-              head_half(acc1, bb4, 64 + hh * 32, dot3);
-              head_finish(dot3, sig_dot, cur, tile, tile_no);
+              for (int i = 0; i < 8; ++i) bn4[i] = __ldg(bp + i);
+            }
+            tmem_ld_wait(acc);
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float4 bb = bb4[c >> 2];
+              const float bc = (c & 3) == 0 ? bb.x : (c & 3) == 1 ? bb.y : (c & 3) == 2 ? bb.z : bb.w;
+              v[c] = fmaxf(__uint_as_float(acc[c]) + bc, 0.f);
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float4* wp = reinterpret_cast<const float4*>(P.aux + AUX_WOUT + o * 128 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 ww = __ldg(wp + i);
+                dot3[o] = fmaf(v[4 * i], ww.x, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 1], ww.y, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 2], ww.z, dot3[o]);
+                dot3[o] = fmaf(v[4 * i + 3], ww.w, dot3[o]);
+              }
+            }
+            if (j == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bb4[i] = bn4[i];
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ARRIVE(BAR_DEMPTY + b);
+          if (S::ENC_ALIASES_ACT && have_next) {
+            // The last layer's MMAs have retired (d_full above), so nothing reads the activation blocks any more: the next
+            // tile's encoding goes into them now, and its layer 0 runs while this tile's head is combined and written out.
+            zero_motion_pads();
+            encode_piece<NET, 0>(smem, nxt, row, hh, exact, lerp, carry);
+            encode_piece<NET, 1>(smem, nxt, row, hh, exact, lerp, carry);
+            if (NET == NET_MOTION) encode_piece<NET, 2>(smem, nxt, row, hh, exact, lerp, carry);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ARRIVE(BAR_AREADY + AREADY_ENC);
+          }
+          // combine the two column halves through shared memory.  With the coarse-pass fusion the tile's FINAL rows go to
+          // `s_part` for the compositing warps, so the half sums travel through the first activation block instead: every
+          // MMA of this tile has retired (d_full above) and the next writer of that block is this very warp group (layer-0
+          // epilogue of the next tile).
+          const bool fused = (NET == NET_SPACE) && !PAIR && P.fuse.on;
+          float* s_half = fused ? reinterpret_cast<float*>(smem + S::act_base) : s_part;
+          if (hh == 1) {
+            s_half[row * 4 + 0] = dot3[0]; s_half[row * 4 + 1] = dot3[1]; s_half[row * 4 + 2] = dot3[2];
+            s_half[row * 4 + 3] = sig_dot;
+          }
+          epi_bar_sync();
+          if (fused && hh == 0) {
+            // the compositing warps must be done with the previous tile's rows (they have had a whole tile period)
+            if (tile_no > 0) mbar_wait(BAR(BAR_RAWEMPTY), (tile_no - 1) & 1);
+            const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
+            const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
+            const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
+            const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
+            reinterpret_cast<float4*>(s_part)[row] = make_float4(o0, o1, o2, sg);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_RAWFULL));
+          }
+          if (hh == 0 && cur.out_index >= 0) {
+            const float o0 = dot3[0] + s_half[row * 4 + 0] + P.aux[AUX_BOUT + 0];
+            const float o1 = dot3[1] + s_half[row * 4 + 1] + P.aux[AUX_BOUT + 1];
+            const float o2 = dot3[2] + s_half[row * 4 + 2] + P.aux[AUX_BOUT + 2];
+            const int oi = cur.out_index;
+            if (NET == NET_SPACE) {
+              const float sg = sig_dot + s_half[row * 4 + 3] + P.aux[AUX_BSIG];
+              if (P.raw) reinterpret_cast<float4*>(P.raw)[oi] = make_float4(o0, o1, o2, sg);
+              if (P.rgb_out) { P.rgb_out[3 * (size_t)oi] = o0; P.rgb_out[3 * (size_t)oi + 1] = o1; P.rgb_out[3 * (size_t)oi + 2] = o2; }
+              if (P.sigma_out) P.sigma_out[oi] = sg;
+            } else {
+              const long long p = tile * TILE_M + row;          // compact point index
+              if (P.flow_out) { P.flow_out[3 * p] = o0; P.flow_out[3 * p + 1] = o1; P.flow_out[3 * p + 2] = o2; }
+              if (P.xyz_out) {                                  // layered_rfrender.py:356 / :510
+                P.xyz_out[3 * p] = __fadd_rn(cur.x, o0);
+                P.xyz_out[3 * p + 1] = __fadd_rn(cur.y, o1);
+                P.xyz_out[3 * p + 2] = __fadd_rn(cur.z, o2);
+              }
+            }
+          }
+          epi_bar_sync();       // the half sums are rewritten by the next tile
 #ifdef STNERF_TIMING
           tm.last_wait += tl1 - tl0; tm.last_epi += clock64() - tl1; tm.tiles += 1;
 #endif
