@@ -362,7 +362,8 @@ def roofline_of(wl, res, precision, steps, peaks):
             "traffic": traffic, "traffic_note": traffic_note, "launches": sp["launches"], "avg_launch_ms": sp["ms"] / max(1, sp["launches"]),
             "share_of_step": sp["ms"] / ms_total,
             "note": "achieved/frac = algorithmic FLOPs (2*MAC/point x points evaluated) / CUDA-event launch durations of this run; the split modes "
-                    "execute %.2f fp16 MMAs per product (frac is capped at 1/%.2f), executed/frac_executed = what the tensor pipe runs" % (terms, terms),
+                    "execute %.2f fp16 MMAs per product (frac = frac_executed / %.2f); executed/frac_executed = what the tensor pipe runs -- the "
+                    "denominator is a cuBLAS rate SUSTAINED UNDER THE POWER CAP, not the silicon peak, so frac_executed may pass 1" % (terms, terms),
             "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "spacenet"}}
     # compositing + resampling kernels: algorithmic bytes (depths + raw rgb-sigma in, depths + images out) against the HBM peak,
     # reported for completeness -- they are instruction-issue-bound (sort / search / scan per sample), see DESIGN.md
