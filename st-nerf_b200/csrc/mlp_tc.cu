@@ -167,24 +167,11 @@ constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);      
 constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);        // SBO 512 B, version 1, SWIZZLE_64B
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 
-#ifndef ISSUE_BRANCH
-#define ISSUE_BRANCH 0                // 0: the stage's instructions are predicated on the elected lane; 1: the other lanes branch around them (A/B)
-#endif
-#if ISSUE_BRANCH
-#define STNERF_ISSUE_SKIP_BRANCH "@!pe bra ISSUE_SKIP_%=;\n\t"
-#define STNERF_ISSUE_SKIP_LABEL "ISSUE_SKIP_%=:\n\t"
-#define STNERF_ISSUE_PRED ""
-#else
-#define STNERF_ISSUE_SKIP_BRANCH ""
-#define STNERF_ISSUE_SKIP_LABEL ""
-#define STNERF_ISSUE_PRED "@pe "
-#endif
 // operands: %0 accumulator (TMEM), %1 A block 0, %2 A block 1, %3 weight stage, %4 instruction descriptor, %5 accumulate flag of the
 // first MMA, %6 barrier to commit to, %7 / %8 descriptor high words (A / B), %9 multicast mask
 #define STNERF_ISSUE_HEAD                                                                                                  \
   "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 da, db0, db1;\n\t.reg .b32 t;\n\t"                                             \
   "elect.sync _|pe, 0xffffffff;\n\t"                                                                                       \
-  STNERF_ISSUE_SKIP_BRANCH                                                                                                 \
   "setp.ne.b32 pa, %5, 0;\n\t"                                                                                             \
   "setp.eq.b32 pt, %5, %5;\n\t"                                                                                            \
   "mov.b64 db0, {%3, %8};\n\t"                                                                                             \
@@ -192,12 +179,12 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
   "mov.b64 db1, {t, %8};\n\t"
 #define STNERF_ISSUE_A(AREG, PFIRST)                                                                                       \
   "mov.b64 da, {" AREG ", %7};\n\t"                                                                                        \
-  STNERF_ISSUE_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db0, %4, " PFIRST ";\n\t"                                              \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db0, %4, " PFIRST ";\n\t"                                              \
   "add.u32 t, " AREG ", 2;\n\t"                                                                                            \
   "mov.b64 da, {t, %7};\n\t"                                                                                               \
-  STNERF_ISSUE_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db1, %4, pt;\n\t"
-#define STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_PRED "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %9;\n\t" STNERF_ISSUE_SKIP_LABEL "}"
-#define STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_PRED "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t" STNERF_ISSUE_SKIP_LABEL "}"
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db1, %4, pt;\n\t"
+#define STNERF_ISSUE_COMMIT_MC "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %9;\n\t}"
+#define STNERF_ISSUE_COMMIT_1 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
 #define STNERF_ISSUE_OPERANDS                                                                                              \
   ::"r"(d_tmem), "r"(a0), "r"(a1), "r"(w), "r"(idesc), "r"(acc0), "r"(bar), "r"(DESC_HI_SW128), "r"(DESC_HI_SW64), "h"(mask) : "memory"
 
