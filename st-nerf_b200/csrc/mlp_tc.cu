@@ -10,7 +10,9 @@
 //     a 4-stage ring with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) from L2;
 //   * every MMA is M=128 x N=256 (or 128) x K=16, so the A tile is re-read from shared memory once per 256 outputs;
 //   * accumulators live in TMEM (two 128x256 fp32 buffers = all 512 columns) so the epilogue of layer k
-//     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1, k-chunk by k-chunk;
+//     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1; the hand-off is per 32-k
+//     SUB-chunk (a_ready[2c + sub]: an epilogue thread owns 16 columns of each half of a 64-column chunk), so the next layer's
+//     first MMAs wait for half a chunk's epilogue, not a whole one;
 //   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which reproduces fp32
 //     products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate); mixed mode keeps that
 //     everywhere the density depends on and runs the colour-only layer rgb_net.1 in one pass;
@@ -29,6 +31,10 @@
 //   * in the coarse pass (n1 = 64: a tile = two whole rays of one layer) two otherwise idle warps composite the tile's rgb / sigma
 //     rows and draw + merge the fine depths (FuseCoarse, resample.cuh): the coarse samples never leave the SM.
 //
+// The producer and the MMA issuer run their loops WARP-WIDE and hand every weight stage to one asm block in which elect.sync picks
+// the issuing lane (issue_stage / load_stage_elect): inside a plain `if (lane == 0)` ptxas wraps each tcgen05 / bulk-copy
+// instruction in an elect-execute-retire loop and the single issuing thread ends up on the critical path (-4.9 % per step).
+//
 // Warp roles (SpaceNet, 384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warps 2..3 = compositing warps
 // (coarse-pass fusion), warps 4..11 = epilogue / encoding warps: warp%4 selects the TMEM lane quarter (row = 32*(warp%4) + lane),
 // (warp-4)/4 the column half of every 64-column chunk and the half of the encoding frequencies the thread computes for its row.
@@ -36,7 +42,8 @@
 //
 // Build flags: SPACE_WSHARE=0 switches the shared weight stream off (every CTA then pulls all 1.8 MB per tile from L2 itself);
 // SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not faster: DESIGN.md 8);
-// MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout (A/B reference).
+// MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout, PRODUCER_ELECT=0 the single-lane weight producer,
+// SPACE_ENC_FIRST=0 the skip layer's original chunk order (A/B references).
 //
 // Restates modeling/spacenet.py:101-160, modeling/motion_net.py:34-71, utils/dimension_kernel.py:24-33.
 #include <cuda_fp16.h>
