@@ -84,11 +84,13 @@ constexpr int SM_ENC = 8 * ABLOCK;           // 2 blocks: hi, lo (SpaceNet).  Mo
 constexpr int SM_RING = 10 * ABLOCK;
 constexpr int SM_MISC = SM_RING + NSTAGE * STAGE_BYTES;
 constexpr int MAX_STAGE = 8;                 // ring slots a kernel may use (CTA-pair mode: 8 half-size stages in the same 64 KB)
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 33, BAR_DEMPTY = 35,
-              BAR_RAWFULL = 37, BAR_RAWEMPTY = 38;                                                                // 39 barriers
-constexpr int N_AREADY = 9, AREADY_ENC = 8;  // a_ready[2c + sub]: 32-k sub-chunk `sub` of activation chunk c written; [8]: the tile's encoding
-constexpr int MISC_TMEM = 312;
-constexpr int MISC_PART = 320;               // float[128][4]: head partial sums of column-half 1; with the coarse-pass fusion: the
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_WPEER = 16, BAR_AREADY = 24, BAR_DFULL = 41, BAR_DEMPTY = 43,
+              BAR_RAWFULL = 45, BAR_RAWEMPTY = 46;                                                                // 47 barriers
+// a_ready[2c + sub]: the fp16 HI half of 32-k sub-chunk `sub` of activation chunk c is written; [8 + 2c + sub]: its LO half;
+// [16]: the tile's encoding (hi and lo)
+constexpr int N_AREADY = 17, AREADY_LO = 8, AREADY_ENC = 16;
+constexpr int MISC_TMEM = 376;
+constexpr int MISC_PART = 384;               // float[128][4]: head partial sums of column-half 1; with the coarse-pass fusion: the
                                              // tile's final (rgb logits, sigma) rows, read by the compositing warps
 constexpr int MISC_CDF = MISC_PART + 2048;   // fused compositing warps: cdf / depth scratch, 2 x 64 floats
 constexpr int SM_TOTAL = SM_MISC + MISC_CDF + 512;
@@ -633,9 +635,11 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
                                                   , EpiTiming& tm
 #endif
 ) {
-  // The thread owns columns [hh*16, hh*16+16) of BOTH 32-column halves of the chunk: after its first 16 columns the first 32-k
-  // sub-chunk of the next layer's A operand is complete (all eight warps arrive on ready_bar), after the second 16 the other one
-  // (ready_bar + 8).  The next layer's MMAs start after HALF a chunk's epilogue -- the per-layer bubble the tensor pipe waits out.
+  // The thread owns columns [hh*16, hh*16+16) of BOTH 32-column halves of the chunk.  Per half ("pass"): the fp16 HI parts of its
+  // 16 columns are stored and announced first (ready_bar + 8*pass: all eight warps arrive), the LO parts and -- layer 6 -- the
+  // density dot product afterwards (ready_bar + 8*(AREADY_LO + pass)).  The next layer's first MMAs (Ahi x Wlo, then Ahi x Whi)
+  // need only the HI half of the first sub-chunk, so the per-layer bubble the tensor pipe waits out is a TMEM load + 16 columns of
+  // bias / ReLU / fp16 conversion + one proxy fence; the LO half is due four MMAs later.
   uint32_t acc[32];
   const int colA = j * 64 + hh * 16, colB = colA + 32;
   TSTAMP(t0);
@@ -660,41 +664,53 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 #endif
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
+    float v[16];
+    uint32_t hp[8];
 #pragma unroll
-    for (int gh = 0; gh < 2; ++gh) {                   // 8 columns -> one 16-byte chunk
-      const int gq = pass * 2 + gh;                    // position in acc / bv / wv
-      uint32_t hp[4], lp[4];
+    for (int e = 0; e < 8; ++e) {                      // HI: bias, ReLU, fp16 -- two 16-byte chunks of 8 columns
+      const int c = pass * 16 + e * 2;
+      const float4 bb = bv[c >> 2];
+      const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
+      v[2 * e] = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
+      v[2 * e + 1] = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
+      hp[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
+    }
+    const uint32_t off0 = sw128_offset(row, pass * 32 + hh * 16), off1 = sw128_offset(row, pass * 32 + hh * 16 + 8);
+    *reinterpret_cast<uint4*>(blk + off0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(blk + off1) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar + 8u * pass); else mbar_arrive(ready_bar + 8u * pass); }
+    if (exact) {                                       // LO: what the fp16 rounding of HI left over
+      uint32_t lp[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = gq * 8 + e * 2;
-        const float4 bb = bv[c >> 2];
-        const float b0 = (c & 2) ? bb.z : bb.x, b1 = (c & 2) ? bb.w : bb.y;
-        const float v0 = fmaxf(__uint_as_float(acc[c]) + b0, 0.f);
-        const float v1 = fmaxf(__uint_as_float(acc[c + 1]) + b1, 0.f);
-        if (SIGMA) {
-          const float4 ww = wv[c >> 2];
-          dot = fmaf(v0, (c & 2) ? ww.z : ww.x, dot);
-          dot = fmaf(v1, (c & 2) ? ww.w : ww.y, dot);
-        }
-        hp[e] = pack_f16x2(v0, v1);
-        if (exact) {
-          const float2 hf = unpack_f16x2(hp[e]);
-          lp[e] = pack_f16x2(v0 - hf.x, v1 - hf.y);
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float2 hf = unpack_f16x2(hp[e]);
+        lp[e] = pack_f16x2(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
       }
-      const uint32_t off = sw128_offset(row, pass * 32 + hh * 16 + gh * 8);
-      *reinterpret_cast<uint4*>(blk + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-      if (exact) *reinterpret_cast<uint4*>(blk + lo_stride + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      *reinterpret_cast<uint4*>(blk + lo_stride + off0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      *reinterpret_cast<uint4*>(blk + lo_stride + off1) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+    }
+    if (SIGMA) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = pass * 16 + e * 2;
+        const float4 ww = wv[c >> 2];
+        dot = fmaf(v[2 * e], (c & 2) ? ww.z : ww.x, dot);
+        dot = fmaf(v[2 * e + 1], (c & 2) ? ww.w : ww.y, dot);
+      }
     }
 #ifdef STNERF_TIMING
     if (pass == 1) t2 = clock64();
 #endif
-    fence_proxy_async();
+    if (exact) fence_proxy_async();
     __syncwarp();
 #ifdef STNERF_TIMING
     if (pass == 1) t3 = clock64();
 #endif
-    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar + 8u * pass); else mbar_arrive(ready_bar + 8u * pass); }
+    if (lane == 0) {
+      if (PAIR) mbar_arrive_cluster(ready_bar + 8u * (AREADY_LO + pass)); else mbar_arrive(ready_bar + 8u * (AREADY_LO + pass));
+    }
   }
 #ifdef STNERF_TIMING
   const long long t4 = clock64();
@@ -852,14 +868,16 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
         // a layer of the stream = correction section [(hi, lo) per 32-k sub-chunk] + main section [hi per sub-chunk] (see the MMA warp)
         const uint8_t* corr = src;
         const uint8_t* mainp = src + (size_t)nsub * 2 * bytes;
-        if (!LOFIRST) {       // interleaved order: the (hi, lo) stages of the correction section serve all three products;
+        // The stream stores (hi, lo) per sub-chunk; the lo stage is CONSUMED first (Ahi*Wlo needs only the HI half of A, which the
+        // epilogue hands over first), so it is loaded first.
+        if (!LOFIRST) {       // interleaved order: the (lo, hi) stages of the correction section serve all three products;
           for (int sc = 0; sc < nsub; ++sc) {                      // single-pass layers never touch the lo stages
-            LOAD(corr + (size_t)(2 * sc) * bytes);
             if (sp) LOAD(corr + (size_t)(2 * sc + 1) * bytes);
+            LOAD(corr + (size_t)(2 * sc) * bytes);
           }
         } else {
           if (sp)
-            for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc) * bytes); LOAD(corr + (size_t)(2 * sc + 1) * bytes); }
+            for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc + 1) * bytes); LOAD(corr + (size_t)(2 * sc) * bytes); }
           for (int sc = 0; sc < nsub; ++sc) LOAD(mainp + (size_t)sc * bytes);
         }
         src = mainp + (size_t)nsub * bytes;
@@ -877,20 +895,21 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const uint32_t mine = PAIR ? bytes / 2 : bytes;     // pair: the rows of this CTA's half of the output columns
           // a layer of the stream = correction section [(hi, lo) per 32-k sub-chunk] + main section [hi per sub-chunk] (see the MMA warp)
           if (!LOFIRST) {     // interleaved order: the (hi, lo) stages of the correction section serve all three products
-            for (int sc = 0; sc < nsub; ++sc)
-              for (int term = 0; term < 2; ++term, src += bytes) {
-                if (term == 1 && !split(l)) continue;          // single-pass layers never touch the lo stages
+            for (int sc = 0; sc < nsub; ++sc, src += 2 * (size_t)bytes)
+              for (int term = 0; term < 2; ++term) {             // the lo stage (stored second) is consumed, hence loaded, first
+                if (term == 0 && !split(l)) continue;            // single-pass layers never touch the lo stages
+                const uint8_t* stage = src + (term == 0 ? bytes : 0u);
                 const uint32_t s = cnt % NST, n = cnt / NST;
                 mbar_wait(BAR(BAR_WEMPTY + s), (n & 1) ^ 1);
                 if (WSHARE) {      // the whole stage lands here (half from this CTA's copy, half from the peer's); this CTA issues its half to both
                   mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
-                  bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), src + rank * (bytes / 2), bytes / 2,
+                  bulk_g2s_mc(sbase + S::ring_base + s * STAGE_STRIDE + rank * (bytes / 2), stage + rank * (bytes / 2), bytes / 2,
                               BAR(BAR_WFULL + s), (uint16_t)3);
                   ++cnt;
                   continue;
                 }
                 mbar_expect_tx(BAR(BAR_WFULL + s), mine);
-                bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, src + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
+                bulk_g2s(sbase + S::ring_base + s * STAGE_STRIDE, stage + (PAIR ? rank * mine : 0u), mine, BAR(BAR_WFULL + s));
                 ++cnt;
               }
             src += (size_t)nsub * bytes;      // the main section is not used
@@ -911,7 +930,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             const uint8_t* corr = src;
             const uint8_t* mainp = src + (size_t)nsub * 2 * bytes;
             if (split(l))
-              for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc) * bytes); LOAD(corr + (size_t)(2 * sc + 1) * bytes); }
+              for (int sc = 0; sc < nsub; ++sc) { LOAD(corr + (size_t)(2 * sc + 1) * bytes); LOAD(corr + (size_t)(2 * sc) * bytes); }
             for (int sc = 0; sc < nsub; ++sc) LOAD(mainp + (size_t)sc * bytes);
             src = mainp + (size_t)nsub * bytes;
           }
@@ -938,7 +957,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     // =============================== MMA issuer: the whole warp runs the loop, one elected lane issues ===============================
     uint32_t cnt = 0;            // weight stages consumed
     uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
-    uint32_t a_par = 0;          // phase parity of a_ready[0..8], one bit each
+    uint32_t a_par = 0;          // phase parity of a_ready[0..16], one bit each
     for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
       for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
         const uint32_t b = g & 1;
@@ -949,16 +968,17 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
         const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
         const bool sp = split(l);
         uint32_t acc = 0;        // the first MMA of the layer overwrites the accumulator
-        // descriptor words of the hi / lo halves of A chunk c (64 k), and the a_ready barrier of its first 32-k sub-chunk (-1: none;
-        // the encoding has ONE arrival phase per tile, waited for at its first use: layer 0, chunk 0, sub-chunk 0)
-        auto a_block = [&](int c, uint32_t& a_hi, uint32_t& a_lo, int& bar0, int& bar1) {
+        // descriptor words of the hi / lo halves of A chunk c (64 k) and the a_ready barriers of its two 32-k sub-chunks: bar[sub] for
+        // the HI half, bar[sub] + AREADY_LO for the LO half (-1: none; the encoding has ONE arrival phase per tile, hi and lo
+        // together, waited for at its first use: layer 0, chunk 0, sub-chunk 0)
+        auto a_block = [&](int c, uint32_t& a_hi, uint32_t& a_lo, int& bar0, int& bar1, bool& has_lo_bar) {
           uint32_t addr, lo_stride;
           if (c < nact) {
-            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar0 = 2 * c; bar1 = 2 * c + 1;
+            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar0 = 2 * c; bar1 = 2 * c + 1; has_lo_bar = true;
           } else {
             const int e = c - nact;
             addr = sbase + S::enc_base + e * ABLOCK; lo_stride = S::ENC_LO_STRIDE;
-            bar0 = (l == 0 && e == 0) ? AREADY_ENC : -1; bar1 = -1;
+            bar0 = (l == 0 && e == 0) ? AREADY_ENC : -1; bar1 = -1; has_lo_bar = false;
           }
           a_hi = desc_lo(addr);
           a_lo = desc_lo(addr + lo_stride);
@@ -985,31 +1005,46 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           acc = 1; ++cnt;
         };
         if (!LOFIRST || !sp) {
-          // interleaved order (and single-pass layers): per 32-k sub-chunk Ahi*Whi and Alo*Whi off the hi stage, Ahi*Wlo off the lo stage
+          // interleaved order (and single-pass layers): per 32-k sub-chunk Ahi*Wlo off the lo stage -- needs only the HI half of A, which
+          // the epilogue delivers first -- then Ahi*Whi and Alo*Whi off the hi stage
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
             int bar[2];
-            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
+            bool lo_bar;
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) {                  // 64 bytes along K = +4 in the address field
               a_wait(bar[sub]);
-              if (sp) { stage4(a_hi + 4 * sub, a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
-              else stage2(a_hi + 4 * sub);
+              if (sp) {
+                stage2(a_hi + 4 * sub);                                // lo weight stage
+                if (lo_bar) a_wait(AREADY_LO + bar[sub]);
+                stage4(a_hi + 4 * sub, a_lo + 4 * sub);                // hi weight stage
+              } else {
+                if (lo_bar) a_wait(AREADY_LO + bar[sub]);              // (keeps the barrier's phase in step; nothing is read)
+                stage2(a_hi + 4 * sub);
+              }
             }
           }
         } else {
-          // corrections first (see the file header): D = Alo*Whi + Ahi*Wlo over the whole K range, then D += Ahi*Whi off the main section
+          // corrections first (see the file header): D = Ahi*Wlo + Alo*Whi over the whole K range, then D += Ahi*Whi off the main section
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
             int bar[2];
-            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
+            bool lo_bar;
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
 #pragma unroll
-            for (uint32_t sub = 0; sub < 2; ++sub) { a_wait(bar[sub]); stage2(a_lo + 4 * sub); stage2(a_hi + 4 * sub); }
+            for (uint32_t sub = 0; sub < 2; ++sub) {
+              a_wait(bar[sub]);
+              stage2(a_hi + 4 * sub);                                  // lo weight stage
+              if (lo_bar) a_wait(AREADY_LO + bar[sub]);
+              stage2(a_lo + 4 * sub);                                  // hi weight stage
+            }
           }
           for (int c = 0; c < nch; ++c) {
             uint32_t a_hi, a_lo;
             int bar[2];
-            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1]);
+            bool lo_bar;
+            a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) stage2(a_hi + 4 * sub);
           }
@@ -1022,7 +1057,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
     if (lane == 0) {
       uint32_t cnt = 0;            // weight stages consumed
       uint32_t g = 0;              // global layer counter (selects the TMEM buffer)
-      uint32_t a_uses[N_AREADY] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t a_uses[N_AREADY] = {};
       auto WAIT = [&](uint32_t bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
       for (long long tile = blockIdx.x; in_range(tile); tile += gridDim.x) {
         for (int l = 0; l < S::N_LAYERS; ++l, ++g) {
@@ -1040,10 +1075,11 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               if (c < nact) {
                 a_hi = sbase + S::act_base + c * ABLOCK;
                 a_lo = a_hi + S::LO_STRIDE;
-                WAIT(BAR(BAR_AREADY + 2 * c), a_uses[2 * c] & 1);          // both 32-k sub-chunks of the chunk
-                ++a_uses[2 * c];
-                WAIT(BAR(BAR_AREADY + 2 * c + 1), a_uses[2 * c + 1] & 1);
-                ++a_uses[2 * c + 1];
+                for (int i = 0; i < 4; ++i) {                        // both 32-k sub-chunks of the chunk, hi and lo halves
+                  const int bi = 2 * c + (i & 1) + (i >> 1) * AREADY_LO;
+                  WAIT(BAR(BAR_AREADY + bi), a_uses[bi] & 1);
+                  ++a_uses[bi];
+                }
               } else {
                 const int e = c - nact;
                 a_hi = sbase + S::enc_base + e * ABLOCK;
@@ -1056,8 +1092,9 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               tc_fence_after();
               for (int sub = 0; sub < 2; ++sub) {
                 const uint32_t a_off = (uint32_t)sub * 64;           // two 32-byte k-steps per 32-wide sub-chunk
-                for (int term = 0; term < 2; ++term) {
+                for (int term = 1; term >= 0; --term) {              // the lo stage comes first in the ring (see the producer)
                   if (term == 1 && !split(l)) continue;
+                  const bool first_mma = (cpos == 0 && sub == 0 && term == (split(l) ? 1 : 0));
                   const uint32_t s = cnt % NST, n = cnt / NST;
                   mbar_wait(BAR(BAR_WFULL + s), n & 1);
                   if (PAIR) mbar_wait_cluster(BAR(BAR_WPEER + s), n & 1);      // ... and the peer's half
@@ -1069,7 +1106,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
                     else umma_f16(d, make_desc_sw128(a_addr + ks * 32), make_desc_sw64(wsm + ks * 32), idesc, acc);
                   };
 #pragma unroll
-                  for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (cpos == 0 && sub == 0 && term == 0 && ks == 0) ? 0u : 1u);
+                  for (int ks = 0; ks < 2; ++ks) MMA(a_hi + a_off, ks, (first_mma && ks == 0) ? 0u : 1u);
                   if (term == 0 && split(l)) {
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) MMA(a_lo + a_off, ks, 1u);
@@ -1093,8 +1130,11 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
                 a_hi = sbase + S::act_base + c * ABLOCK;
                 a_lo = a_hi + S::LO_STRIDE;
                 if (wait) {
-                  WAIT(BAR(BAR_AREADY + 2 * c), a_uses[2 * c] & 1); ++a_uses[2 * c];
-                  WAIT(BAR(BAR_AREADY + 2 * c + 1), a_uses[2 * c + 1] & 1); ++a_uses[2 * c + 1];
+                  for (int i = 0; i < 4; ++i) {                      // both 32-k sub-chunks of the chunk, hi and lo halves
+                    const int bi = 2 * c + (i & 1) + (i >> 1) * AREADY_LO;
+                    WAIT(BAR(BAR_AREADY + bi), a_uses[bi] & 1);
+                    ++a_uses[bi];
+                  }
                 }
               } else {
                 const int e = c - nact;
@@ -1131,9 +1171,9 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               for (int c = 0; c < nch; ++c) {
                 uint32_t a_hi, a_lo;
                 chunk((S::enc_first(l) && nact > 0 && nch > nact) ? (c == 0 ? nact : c - 1) : c, true, a_hi, a_lo);
-                for (int sub = 0; sub < 2; ++sub) {                  // correction pass: D = Alo*Whi + Ahi*Wlo
-                  STAGE(a_lo + (uint32_t)sub * 64);                  // hi weight stage
+                for (int sub = 0; sub < 2; ++sub) {                  // correction pass: D = Ahi*Wlo + Alo*Whi
                   STAGE(a_hi + (uint32_t)sub * 64);                  // lo weight stage
+                  STAGE(a_lo + (uint32_t)sub * 64);                  // hi weight stage
                 }
               }
             }
