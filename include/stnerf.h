@@ -223,6 +223,10 @@ int stnerf_selftest_umma(float* max_err_host);
 int stnerf_selftest_umma_accum(int reps, float* max_err_host, float* mean_signed_rel_err_host);
 /* The same through the CTA-pair protocol (`tcgen05.mma.cta_group::2`, M = 256 over the two CTAs of a cluster: remote mbarrier
  * arrives, multicast commit, paired TMEM allocation): one 256x256x64 product; expected < 1e-3.                 */
+/* The same 128x256x64 product with the A operand in TENSOR memory: written with tcgen05.st in the layout the SpaceNet epilogue
+ * uses for the next layer's activations (8 columns of fp16 pairs per K=16 step at a 16-column pitch), read by
+ * tcgen05.mma [d], [a], b-desc.  Pins that layout on the device the library runs on. */
+int stnerf_selftest_umma_ts(float* max_err_host);
 int stnerf_selftest_umma_pair(float* max_err_host);
 
 /* Diagnostic read-back of the sample depths of the LAST chunk rendered by stnerf_render (parity tooling: which depths did

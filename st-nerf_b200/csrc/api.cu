@@ -910,6 +910,11 @@ int stnerf_selftest_umma(float* max_err_host) {
   return tc_selftest(max_err_host);
 }
 
+int stnerf_selftest_umma_ts(float* max_err_host) {
+  if (!max_err_host) return STNERF_EINVAL;
+  return tc_selftest_ts(max_err_host);
+}
+
 int stnerf_selftest_umma_accum(int reps, float* max_err_host, float* mean_signed_rel_err_host) {
   if (!max_err_host || !mean_signed_rel_err_host || reps < 1 || reps > 4096) return STNERF_EINVAL;
   return tc_selftest_accum(reps, max_err_host, mean_signed_rel_err_host);

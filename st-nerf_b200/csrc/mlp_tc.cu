@@ -3,16 +3,22 @@
 //
 // Persistent CTAs (SpaceNet: one per SM; MotionNet: two per SM, see Sched<NET_MOTION>) walk tiles of 128 points.  Per tile the
 // whole network runs on-chip:
-//   * activations (A operand) live in shared memory as fp16 hi/lo pairs in the canonical 128B-swizzled K-major
-//     UMMA layout ([128 rows x 64 k] blocks); they never leave the SM between layers;
+//   * SpaceNet hidden activations (A operand) never leave TENSOR MEMORY (SPACE_A_TMEM, default): the epilogue converts a layer's
+//     fp32 accumulator columns IN PLACE into fp16 hi/lo pairs (tcgen05.ld -> bias -> ReLU -> split -> tcgen05.st: the 16 fp32
+//     columns of one K=16 step become 8 columns of hi pairs + 8 of lo pairs) and the next layer's MMAs read them from there
+//     (tcgen05.mma [d], [a], b-desc) while accumulating into the other buffer -- the two 128x256 buffers alternate between
+//     "accumulator" and "A operand", shared memory only holds the input encoding and the weight ring;
+//   * MotionNet (and the SPACE_A_TMEM=0 / CTA-pair builds) keep the activations in shared memory as fp16 hi/lo pairs in the
+//     canonical 128B-swizzled K-major UMMA layout ([128 rows x 64 k] blocks); the encoding always lives there;
 //   * weights (B operand) are pre-packed on the host into [N out-rows x 32 k] fp16 blocks (N = 256 or 128) that are
 //     already the 64B-swizzled shared-memory image, in the exact order the MMA warp consumes them, and stream through
-//     a 4-stage ring with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) from L2;
-//   * every MMA is M=128 x N=256 (or 128) x K=16, so the A tile is re-read from shared memory once per 256 outputs;
+//     a ring of 16 KB stages (SpaceNet: 8; MotionNet: 4 x 8 KB) with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) from L2;
+//   * every MMA is M=128 x N=256 (or 128) x K=16;
 //   * accumulators live in TMEM (two 128x256 fp32 buffers = all 512 columns) so the epilogue of layer k
-//     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> st.shared) overlaps the MMAs of layer k+1; the hand-off is per 32-k
-//     SUB-chunk (a_ready[2c + sub]: an epilogue thread owns 16 columns of each half of a 64-column chunk), so the next layer's
-//     first MMAs wait for half a chunk's epilogue, not a whole one;
+//     (tcgen05.ld -> bias -> ReLU -> fp16 hi/lo split -> store) overlaps the MMAs of layer k+1; the hand-off is per 32-k
+//     SUB-chunk and per HALF (a_ready[2c + sub]: the fp16 hi parts, a_ready[8 + 2c + sub]: the lo parts; an epilogue thread owns
+//     16 columns of each half of a 64-column chunk): the next layer opens with Ahi*Wlo off the lo weight stage, which needs the hi
+//     parts only, so its first MMAs wait for a TMEM load + 16 columns of bias / ReLU / conversion, not for a whole chunk;
 //   * exact mode issues three fp16 MMAs per product, D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulate), which reproduces fp32
 //     products to ~2^-22 (the only tensor-core formulation inside the 1e-3 gate); mixed mode keeps that
 //     everywhere the density depends on and runs the colour-only layer rgb_net.1 in one pass;
@@ -40,7 +46,9 @@
 // (warp-4)/4 the column half of every 64-column chunk and the half of the encoding frequencies the thread computes for its row.
 // (MotionNet, 320 threads: the same roles without warps 2..3, epilogue warps 2..9.)
 //
-// Build flags: SPACE_WSHARE=0 switches the shared weight stream off (every CTA then pulls all 1.8 MB per tile from L2 itself);
+// Build flags: SPACE_A_TMEM=0 keeps the SpaceNet activations in shared memory (A/B reference: bit-identical results, same speed --
+// the kernel is bound by the power cap, not by the shared-memory port: profiles/r02_ab_a_in_tmem.json), SPACE_RING the depth of
+// the SpaceNet weight ring under SPACE_A_TMEM (8; the shared-memory build has room for 4); SPACE_WSHARE=0 switches the shared weight stream off (every CTA then pulls all 1.8 MB per tile from L2 itself);
 // SPACE_CTA_PAIR=1 runs the SpaceNet tiles as 2-CTA clusters on one cta_group::2 accumulator (correct, not faster: DESIGN.md 8);
 // MOTION_CTAS_PER_SM=1 restores the single-CTA MotionNet layout, PRODUCER_ELECT=0 the single-lane weight producer,
 // SPACE_ENC_FIRST=0 the skip layer's original chunk order (A/B references).
@@ -62,6 +70,13 @@ namespace {
 #define SPACE_WSHARE 1                // 1 (default): SpaceNet CTAs run as 2-CTA clusters that SHARE THE WEIGHT STREAM: each CTA pulls half of
 #endif                                //    every stage from L2 and multicasts it into both shared memories (MMAs stay per CTA, cta_group::1);
                                       //    0: every CTA streams all weights itself (A/B reference)
+#ifndef SPACE_A_TMEM
+#define SPACE_A_TMEM 1                // 1 (default): the SpaceNet hidden activations never leave TENSOR MEMORY: the epilogue converts a layer's
+#endif                                //    fp32 accumulator columns IN PLACE into the fp16 hi/lo A operand of the next layer (tcgen05.st) and
+                                      //    the MMAs read A from tensor memory (tcgen05.mma [d], [a], b-desc); 0: A through shared memory (A/B)
+#ifndef SPACE_RING
+#define SPACE_RING 8                  // weight-ring depth of the SpaceNet kernel under SPACE_A_TMEM (16 KB stages; the activations' 128 KB are free)
+#endif
 #ifndef SPACE_ENC_FIRST
 #define SPACE_ENC_FIRST 1             // 1 (default): the SpaceNet skip layer consumes its encoding chunk first (Sched::enc_first; 0: last, A/B)
 #endif
@@ -163,6 +178,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// A operand in tensor memory ([128 lanes x 8 columns] of fp16 pairs at a_tmem), B through its shared-memory descriptor
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -211,6 +235,31 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t a0, uint32
   if (NA == 2 && !MC)
     asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A("%1", "pa") STNERF_ISSUE_A("%2", "pt") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
 }
+// The same with the A operand in TENSOR memory (SPACE_A_TMEM): a0 / a1 are tensor-memory addresses of [128 lanes x 8 columns] fp16x2
+// slices (row = lane, column c = k elements 2c, 2c+1); the second K=16 step of the stage sits 16 columns further (8 hi + 8 lo columns
+// per 16 k, see epi_hidden_chunk).
+#define STNERF_ISSUE_A_TS(AREG, PFIRST)                                                                                    \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [" AREG "], db0, %4, " PFIRST ";\n\t"                                      \
+  "add.u32 t, " AREG ", 16;\n\t"                                                                                           \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [t], db1, %4, pt;\n\t"
+template <int NA, bool MC>
+__device__ __forceinline__ void issue_stage_ts(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t w, uint32_t idesc, uint32_t acc0,
+                                               uint32_t bar) {
+  const uint16_t mask = 3;
+  if (NA == 1 && MC) asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A_TS("%1", "pa") STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_OPERANDS);
+  if (NA == 1 && !MC) asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A_TS("%1", "pa") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
+  if (NA == 2 && MC)
+    asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A_TS("%1", "pa") STNERF_ISSUE_A_TS("%2", "pt") STNERF_ISSUE_COMMIT_MC STNERF_ISSUE_OPERANDS);
+  if (NA == 2 && !MC)
+    asm volatile(STNERF_ISSUE_HEAD STNERF_ISSUE_A_TS("%1", "pa") STNERF_ISSUE_A_TS("%2", "pt") STNERF_ISSUE_COMMIT_1 STNERF_ISSUE_OPERANDS);
+}
+// eight 32-bit columns of this thread's lane (row) -> tensor memory; the wait makes the warp's stores visible to later tcgen05 ops
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // tcgen05.commit by one elected lane of the converged warp ("every MMA issued so far has retired" -> one arrival on `bar`)
 __device__ __forceinline__ void commit_elect(uint32_t bar) {
   asm volatile(
@@ -363,7 +412,19 @@ enum { NET_SPACE = 0, NET_MOTION = 1 };
 template <int NET> struct Sched;
 template <> struct Sched<NET_SPACE> {
   static constexpr int N_LAYERS = 8;
-  static constexpr int act_base = SM_ACT, enc_base = SM_ENC;
+#if SPACE_A_TMEM && !SPACE_CTA_PAIR
+  // hidden activations in tensor memory: shared memory holds the encoding (2 blocks), a 4 KB scratch (head half sums) and a
+  // SPACE_RING-deep weight ring
+  static constexpr int act_base = 0, enc_base = 0, scratch_base = 2 * ABLOCK;
+  static constexpr int n_stage = SPACE_RING;
+  static constexpr int ring_base = 2 * ABLOCK + 4096, stage_bytes = STAGE_BYTES, misc_base = ring_base + n_stage * STAGE_BYTES,
+                       smem_total = misc_base + MISC_CDF + 512;
+  static_assert(n_stage <= MAX_STAGE && smem_total <= 232448, "SpaceNet ring");
+#else
+  static constexpr int act_base = SM_ACT, enc_base = SM_ENC, scratch_base = SM_ACT;
+  static constexpr int n_stage = NSTAGE;
+  static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
+#endif
   static constexpr int LO_STRIDE = 4 * ABLOCK;          // ACT lo blocks follow the 4 hi blocks
   static constexpr int ENC_LO_STRIDE = ABLOCK;
   static constexpr int ENC_LAST_USE = 4;                // last layer whose MMAs read the encoding buffer
@@ -375,11 +436,11 @@ template <> struct Sched<NET_SPACE> {
   __host__ __device__ static constexpr bool enc_first(int l) { return SPACE_ENC_FIRST != 0 && l == 4; }
   // CTA shape and shared/tensor-memory map: one CTA per SM, the whole 227 KB and all 512 TMEM columns
   static constexpr int N_THREADS = NTHREADS, EPI_W0 = EPI_WARP0, CTAS_PER_SM = 1;
-  static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
   static constexpr int tmem_cols = 512, d_stride = 256;
   static constexpr bool ENC_ALIASES_ACT = false;
 };
 template <> struct Sched<NET_MOTION> {
+  static constexpr int n_stage = NSTAGE;
   static constexpr int N_LAYERS = 5;
   static constexpr int LO_STRIDE = 2 * ABLOCK;
   static constexpr int ENC_LO_STRIDE = 2 * ABLOCK;
@@ -394,14 +455,14 @@ template <> struct Sched<NET_MOTION> {
   // fills those gaps.  Budget per CTA: 100 KB of shared memory (the encoding shares the activation blocks -- it is
   // written after the last layer's MMAs have retired -- and the N=128 weight stages are 8 KB), 256 TMEM columns
   // (2 x 128 accumulators), 10 warps (no spare warps) so that 2 x 320 threads leave 96 registers per thread.
-  static constexpr int act_base = SM_ACT, enc_base = SM_ACT;
+  static constexpr int act_base = SM_ACT, enc_base = SM_ACT, scratch_base = SM_ACT;
   static constexpr int N_THREADS = 320, EPI_W0 = 2, CTAS_PER_SM = 2;
   static constexpr int ring_base = 4 * ABLOCK, stage_bytes = 8192, misc_base = ring_base + NSTAGE * stage_bytes,
                        smem_total = misc_base + MISC_CDF;
   static constexpr int tmem_cols = 256, d_stride = 128;
   static constexpr bool ENC_ALIASES_ACT = true;
 #else
-  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * ABLOCK;
+  static constexpr int act_base = SM_ACT, enc_base = SM_ACT + 4 * ABLOCK, scratch_base = SM_ACT;
   static constexpr int N_THREADS = NTHREADS, EPI_W0 = EPI_WARP0, CTAS_PER_SM = 1;
   static constexpr int ring_base = SM_RING, stage_bytes = STAGE_BYTES, misc_base = SM_MISC, smem_total = SM_TOTAL;
   static constexpr int tmem_cols = 512, d_stride = 256;
@@ -627,7 +688,7 @@ struct EpiTiming { long long ld = 0, math = 0, fence = 0, arrive = 0, wait_dfull
 #define TSTAMP(x)
 #endif
 
-template <bool SIGMA, bool PAIR = false>
+template <bool SIGMA, bool PAIR = false, bool ATMEM = false>
 __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, int row, const float* __restrict__ bias,
                                                   const float* __restrict__ wdot, uint8_t* blk, int lo_stride, bool exact,
                                                   int lane, uint32_t ready_bar, float dot
@@ -640,6 +701,9 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
   // density dot product afterwards (ready_bar + 8*(AREADY_LO + pass)).  The next layer's first MMAs (Ahi x Wlo, then Ahi x Whi)
   // need only the HI half of the first sub-chunk, so the per-layer bubble the tensor pipe waits out is a TMEM load + 16 columns of
   // bias / ReLU / fp16 conversion + one proxy fence; the LO half is due four MMAs later.
+  // ATMEM: the operand goes back into TENSOR memory, in place of the fp32 columns it was computed from -- the thread's 16 accumulator
+  // columns [c0, c0+16) of a pass become 8 columns of packed HI pairs [c0, c0+8) and 8 of LO pairs [c0+8, c0+16): one K=16 step of
+  // the next layer's A operand (k = c0 .. c0+15; column e holds k = c0+2e in its low half, c0+2e+1 in its high half).
   uint32_t acc[32];
   const int colA = j * 64 + hh * 16, colB = colA + 32;
   TSTAMP(t0);
@@ -676,9 +740,16 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
       hp[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
     }
     const uint32_t off0 = sw128_offset(row, pass * 32 + hh * 16), off1 = sw128_offset(row, pass * 32 + hh * 16 + 8);
-    *reinterpret_cast<uint4*>(blk + off0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-    *reinterpret_cast<uint4*>(blk + off1) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-    fence_proxy_async();
+    const uint32_t tcol = dcol + (uint32_t)(pass ? colB : colA);
+    if (ATMEM) {
+      tmem_st8(tcol, hp);
+      tmem_st_wait();
+      tc_fence_before();
+    } else {
+      *reinterpret_cast<uint4*>(blk + off0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(blk + off1) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      fence_proxy_async();
+    }
     __syncwarp();
     if (lane == 0) { if (PAIR) mbar_arrive_cluster(ready_bar + 8u * pass); else mbar_arrive(ready_bar + 8u * pass); }
     if (exact) {                                       // LO: what the fp16 rounding of HI left over
@@ -688,8 +759,12 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
         const float2 hf = unpack_f16x2(hp[e]);
         lp[e] = pack_f16x2(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
       }
-      *reinterpret_cast<uint4*>(blk + lo_stride + off0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-      *reinterpret_cast<uint4*>(blk + lo_stride + off1) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+      if (ATMEM) {
+        tmem_st8(tcol + 8u, lp);
+      } else {
+        *reinterpret_cast<uint4*>(blk + lo_stride + off0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        *reinterpret_cast<uint4*>(blk + lo_stride + off1) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+      }
     }
     if (SIGMA) {
 #pragma unroll
@@ -703,7 +778,12 @@ __device__ __forceinline__ float epi_hidden_chunk(uint32_t dcol, int j, int hh, 
 #ifdef STNERF_TIMING
     if (pass == 1) t2 = clock64();
 #endif
-    if (exact) fence_proxy_async();
+    if (ATMEM) {
+      if (exact) tmem_st_wait();
+      tc_fence_before();
+    } else if (exact) {
+      fence_proxy_async();
+    }
     __syncwarp();
 #ifdef STNERF_TIMING
     if (pass == 1) t3 = clock64();
@@ -817,6 +897,8 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   // 3-term split for layer l?  (mixed mode: everything the density depends on is split, the colour-only layer is not)
   const bool single_last = P.single_last != 0;
   auto split = [&](int l) { return exact && !(single_last && l == S::N_LAYERS - 1); };
+  // hidden activations in tensor memory (see SPACE_A_TMEM); the encoding chunks (layer 0, skip layer) stay in shared memory
+  constexpr bool ATMEM = (NET == NET_SPACE) && !PAIR && (SPACE_A_TMEM != 0);
   constexpr bool lo_first = LOFIRST;      // order of the split MMAs: a compile-time variant, the interleaved default pays nothing for it
   const long long n_points = src_num_points(P.src);
   const long long n_tiles = (n_points + TILE_M - 1) / TILE_M;
@@ -824,7 +906,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
   constexpr uint32_t N_ARRIVE = PAIR ? 2 * N_EPI_WARPS : N_EPI_WARPS;      // epilogue warps of both CTAs report to the leader
   // weight ring: a CTA of a pair holds half of every stage, so the same 64 KB give twice the slots -- the extra depth pays
   // for the relay hop (peer's copy lands -> remote arrive -> leader) on top of the L2 latency
-  constexpr uint32_t NST = PAIR ? 2 * NSTAGE : NSTAGE;
+  constexpr uint32_t NST = PAIR ? 2 * NSTAGE : S::n_stage;
   constexpr uint32_t STAGE_STRIDE = PAIR ? S::stage_bytes / 2 : S::stage_bytes;
   static_assert(NST <= MAX_STAGE, "barrier slots");
   if (tid == 0) {
@@ -968,13 +1050,26 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
         const int nact = S::act_chunks(l), nch = nact + S::enc_chunks(l);
         const bool sp = split(l);
         uint32_t acc = 0;        // the first MMA of the layer overwrites the accumulator
+        // ATMEM: this layer's accumulator buffer is the one the PREVIOUS layer's MMAs read their A operand from.  A layer that opens
+        // with an activation chunk waits for the previous layer's epilogue anyway (hence for d_full); one that opens with the
+        // encoding (layer 0 after the last layer of the previous tile, the skip layer) waits for the previous MMAs to retire here.
+        if (ATMEM && g > 0 && (l == 0 || S::enc_first(l))) {
+          mbar_wait(BAR(BAR_DFULL + (b ^ 1u)), ((g - 1) >> 1) & 1);
+          tc_fence_after();
+        }
         // descriptor words of the hi / lo halves of A chunk c (64 k) and the a_ready barriers of its two 32-k sub-chunks: bar[sub] for
         // the HI half, bar[sub] + AREADY_LO for the LO half (-1: none; the encoding has ONE arrival phase per tile, hi and lo
         // together, waited for at its first use: layer 0, chunk 0, sub-chunk 0)
         auto a_block = [&](int c, uint32_t& a_hi, uint32_t& a_lo, int& bar0, int& bar1, bool& has_lo_bar) {
           uint32_t addr, lo_stride;
           if (c < nact) {
-            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE; bar0 = 2 * c; bar1 = 2 * c + 1; has_lo_bar = true;
+            bar0 = 2 * c; bar1 = 2 * c + 1; has_lo_bar = true;
+            if (ATMEM) {       // the previous layer's accumulator buffer, converted in place: tensor-memory column of k = 64 c
+              a_hi = tmem_base + (b ^ 1u) * S::d_stride + (uint32_t)c * 64u;
+              a_lo = a_hi + 8u;
+              return;
+            }
+            addr = sbase + S::act_base + c * ABLOCK; lo_stride = S::LO_STRIDE;
           } else {
             const int e = c - nact;
             addr = sbase + S::enc_base + e * ABLOCK; lo_stride = S::ENC_LO_STRIDE;
@@ -992,16 +1087,19 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           tc_fence_after();
         };
         // the next weight stage of the stream times the 32-k slice(s) of A at descriptor word(s) a0 (and a1)
-        auto stage2 = [&](uint32_t a0) {
+        // (ts: the slices are tensor-memory addresses -- activation chunks under ATMEM)
+        auto stage2 = [&](uint32_t a0, bool ts) {
           const uint32_t s = cnt % NST, n = cnt / NST;
           mbar_wait(BAR(BAR_WFULL + s), n & 1);
-          issue_stage<1, WSHARE>(d, a0, a0, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          if (ATMEM && ts) issue_stage_ts<1, WSHARE>(d, a0, a0, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          else issue_stage<1, WSHARE>(d, a0, a0, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
           acc = 1; ++cnt;
         };
-        auto stage4 = [&](uint32_t a0, uint32_t a1) {
+        auto stage4 = [&](uint32_t a0, uint32_t a1, bool ts) {
           const uint32_t s = cnt % NST, n = cnt / NST;
           mbar_wait(BAR(BAR_WFULL + s), n & 1);
-          issue_stage<2, WSHARE>(d, a0, a1, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          if (ATMEM && ts) issue_stage_ts<2, WSHARE>(d, a0, a1, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
+          else issue_stage<2, WSHARE>(d, a0, a1, desc_lo(sbase + S::ring_base + s * STAGE_STRIDE), idesc, acc, BAR(BAR_WEMPTY + s));
           acc = 1; ++cnt;
         };
         if (!LOFIRST || !sp) {
@@ -1012,16 +1110,18 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             int bar[2];
             bool lo_bar;
             a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
+            const bool ts = ATMEM && lo_bar;                          // activation chunk in tensor memory
+            const uint32_t sstep = ts ? 32u : 4u;                     // next 32-k sub-chunk: 32 columns / 64 bytes along K (+4 in the address field)
 #pragma unroll
-            for (uint32_t sub = 0; sub < 2; ++sub) {                  // 64 bytes along K = +4 in the address field
+            for (uint32_t sub = 0; sub < 2; ++sub) {
               a_wait(bar[sub]);
               if (sp) {
-                stage2(a_hi + 4 * sub);                                // lo weight stage
+                stage2(a_hi + sstep * sub, ts);                        // lo weight stage
                 if (lo_bar) a_wait(AREADY_LO + bar[sub]);
-                stage4(a_hi + 4 * sub, a_lo + 4 * sub);                // hi weight stage
+                stage4(a_hi + sstep * sub, a_lo + sstep * sub, ts);    // hi weight stage
               } else {
                 if (lo_bar) a_wait(AREADY_LO + bar[sub]);              // (keeps the barrier's phase in step; nothing is read)
-                stage2(a_hi + 4 * sub);
+                stage2(a_hi + sstep * sub, ts);
               }
             }
           }
@@ -1032,12 +1132,14 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             int bar[2];
             bool lo_bar;
             a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
+            const bool ts = ATMEM && lo_bar;
+            const uint32_t sstep = ts ? 32u : 4u;
 #pragma unroll
             for (uint32_t sub = 0; sub < 2; ++sub) {
               a_wait(bar[sub]);
-              stage2(a_hi + 4 * sub);                                  // lo weight stage
+              stage2(a_hi + sstep * sub, ts);                          // lo weight stage
               if (lo_bar) a_wait(AREADY_LO + bar[sub]);
-              stage2(a_lo + 4 * sub);                                  // hi weight stage
+              stage2(a_lo + sstep * sub, ts);                          // hi weight stage
             }
           }
           for (int c = 0; c < nch; ++c) {
@@ -1045,8 +1147,10 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
             int bar[2];
             bool lo_bar;
             a_block(chunk_at(c), a_hi, a_lo, bar[0], bar[1], lo_bar);
+            const bool ts = ATMEM && lo_bar;
+            const uint32_t sstep = ts ? 32u : 4u;
 #pragma unroll
-            for (uint32_t sub = 0; sub < 2; ++sub) stage2(a_hi + 4 * sub);
+            for (uint32_t sub = 0; sub < 2; ++sub) stage2(a_hi + sstep * sub, ts);
           }
         }
         commit_elect(BAR(BAR_DFULL + b));                              // accumulator of layer g complete
@@ -1255,7 +1359,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           const int nchunk = width / 64;
           if (NET == NET_SPACE && l == 6) {
             for (int j = 0; j < nchunk; ++j)
-              sig_dot = epi_hidden_chunk<true, PAIR>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
+              sig_dot = epi_hidden_chunk<true, PAIR, ATMEM>(dcol, j, hh, row, bias, P.aux + AUX_WSIG, smem + S::act_base + j * ABLOCK,
                                                      S::LO_STRIDE, split(l + 1), lane, LBAR(BAR_AREADY + 2 * j), sig_dot
 #ifdef STNERF_TIMING
                                                , tm
@@ -1263,7 +1367,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
               );
           } else {
             for (int j = 0; j < nchunk; ++j)
-              epi_hidden_chunk<false, PAIR>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, split(l + 1),
+              epi_hidden_chunk<false, PAIR, ATMEM>(dcol, j, hh, row, bias, nullptr, smem + S::act_base + j * ABLOCK, S::LO_STRIDE, split(l + 1),
                                             lane, LBAR(BAR_AREADY + 2 * j), 0.f
 #ifdef STNERF_TIMING
                                       , tm
@@ -1366,7 +1470,7 @@ __global__ void __launch_bounds__(Sched<NET>::N_THREADS, Sched<NET>::CTAS_PER_SM
           // MMA of this tile has retired (d_full above) and the next writer of that block is this very warp group (layer-0
           // epilogue of the next tile).
           const bool fused = (NET == NET_SPACE) && !PAIR && P.fuse.on;
-          float* s_half = fused ? reinterpret_cast<float*>(smem + S::act_base) : s_part;
+          float* s_half = fused ? reinterpret_cast<float*>(smem + S::scratch_base) : s_part;
           if (hh == 1) {
             s_half[row * 4 + 0] = dot3[0]; s_half[row * 4 + 1] = dot3[1]; s_half[row * 4 + 2] = dot3[2];
             s_half[row * 4 + 3] = sig_dot;
@@ -1498,7 +1602,9 @@ __global__ void __launch_bounds__(128) head_bias_kernel(PointSrc src, const floa
 // self-test: 128 x N x 64 fp16 UMMA (N = 256) through exactly the descriptors / swizzles / bulk copy / TMEM load used above
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bstages,
-                                                              float* __restrict__ D, int reps) {
+                                                              float* __restrict__ D, int reps, int ts) {
+  // ts != 0: the A operand goes through TENSOR memory in the layout of the SpaceNet epilogue (SPACE_A_TMEM): per K=16 step 8 columns
+  // of packed fp16 pairs at a 16-column pitch, written with tcgen05.st, read by tcgen05.mma [d], [a], b-desc
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar = sbase + ABLOCK + 2 * STAGE_BYTES, bar2 = bar + 8;
@@ -1510,7 +1616,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     mbar_init(bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
   // A: row `tid`, 64 columns, written with the epilogue's store path (hi only)
   for (int c0 = 0; c0 < 64; c0 += 32) {
     float v[32];
@@ -1522,7 +1628,30 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) {
+  if (ts) {
+    for (int k4 = 0; k4 < 4; ++k4) {
+      uint32_t hp[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hp[e] = pack_f16x2(A[tid * 64 + k4 * 16 + 2 * e], A[tid * 64 + k4 * 16 + 2 * e + 1]);
+      tmem_st8(tmem_base + ((uint32_t)(warp * 32) << 16) + 256u + 16u * k4, hp);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (tid == 0 && ts) {
+    mbar_expect_tx(bar2, 2 * STAGE_BYTES);
+    bulk_g2s(sbase + ABLOCK, Bstages, 2 * STAGE_BYTES, bar2);
+    mbar_wait(bar2, 0);
+    tc_fence_after();
+    for (int rep = 0; rep < reps; ++rep)
+      for (int sub = 0; sub < 2; ++sub)
+        for (int ks = 0; ks < 2; ++ks)
+          umma_f16_ts(tmem_base, tmem_base + 256u + 32u * sub + 16u * ks,
+                      make_desc_sw64(sbase + ABLOCK + sub * STAGE_BYTES + ks * 32), idesc_n(256), (rep | sub | ks) ? 1u : 0u);
+    umma_commit(bar);
+  } else if (tid == 0) {
     mbar_expect_tx(bar2, 2 * STAGE_BYTES);                       // two 32-wide k sub-chunks
     bulk_g2s(sbase + ABLOCK, Bstages, 2 * STAGE_BYTES, bar2);
     mbar_wait(bar2, 0);
@@ -1545,7 +1674,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1788,7 +1917,7 @@ int tc_pack_motionnet(TcNet& net, const float* p) {
 // reps > 1 (accumulation probe): all-positive operands, the product accumulated `reps` times into the same TMEM accumulator
 // (4*reps MMAs of K=16); reports the max and the MEAN SIGNED relative error against the fp64 sum -- a negative mean that grows
 // with reps is the signature of round-toward-zero accumulation inside the tensor core.
-int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host) {
+int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host, int ts) {
   std::vector<float> Af(128 * 64), Bf(256 * 64);
   uint32_t s = 12345u;
   const bool probe = reps > 1;
@@ -1810,7 +1939,7 @@ int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host
   STNERF_CUDA(cudaMemcpy(dB, stages.data(), stages.size(), cudaMemcpyHostToDevice));
   const int smem = ABLOCK + 2 * STAGE_BYTES + 64;
   STNERF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, reps);
+  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, reps, ts);
   STNERF_LAUNCH_CHECK();
   STNERF_CUDA(cudaDeviceSynchronize());
   std::vector<float> D(128 * 256);
@@ -1830,7 +1959,8 @@ int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host
   if (mean_signed_rel_host) *mean_signed_rel_host = (float)(signed_rel / (128.0 * 256.0));
   return STNERF_OK;
 }
-int tc_selftest(float* max_err_host) { return tc_selftest_accum(1, max_err_host, nullptr); }
+int tc_selftest(float* max_err_host) { return tc_selftest_accum(1, max_err_host, nullptr, 0); }
+int tc_selftest_ts(float* max_err_host) { return tc_selftest_accum(1, max_err_host, nullptr, 1); }
 
 // The same for the CTA-pair protocol: 256 x 256 x 64.
 int tc_selftest_pair(float* max_err_host) {

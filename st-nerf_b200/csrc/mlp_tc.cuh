@@ -45,7 +45,8 @@ size_t tc_tail_floats(bool is_space);
 int tc_export(const TcNet& net, bool is_space, uint8_t* stream_host, float* aux_host, float* tail_host);
 int tc_import(TcNet& net, bool is_space, int use_time, const uint8_t* stream_host, const float* aux_host, const float* tail_host);
 int tc_selftest(float* max_err_host);   // one 128x128x64 UMMA vs a host reference
-int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host);   // accumulation probe (see mlp_tc.cu)
+int tc_selftest_ts(float* max_err_host);   // the same product with the A operand in tensor memory (tcgen05.st layout of the SpaceNet epilogue)
+int tc_selftest_accum(int reps, float* max_err_host, float* mean_signed_rel_host, int ts = 0);   // accumulation probe (see mlp_tc.cu)
 int tc_selftest_pair(float* max_err_host);   // 256x256x64 through one cta_group::2 accumulator (two CTAs of a cluster)
 int tc_launch_spacenet(const PointSrc& src, const TcNet& net, const SpaceNetW& w32, int precision, float* cbuf, float* raw,
                        float* rgb_out, float* sigma_out, int num_sms, cudaStream_t st, const FuseCoarse* fuse = nullptr,

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "stnerf_set_ray_ids": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64]),
     "stnerf_selftest_umma": (C.c_int, [C.POINTER(C.c_float)]),
     "stnerf_selftest_umma_pair": (C.c_int, [C.POINTER(C.c_float)]),
+    "stnerf_selftest_umma_ts": (C.c_int, [C.POINTER(C.c_float)]),
     "stnerf_selftest_umma_accum": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "stnerf_profile_begin": (C.c_int, [_P]),
     "stnerf_profile_end": (C.c_int, [_P, C.POINTER(Profile)]),

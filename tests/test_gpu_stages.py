@@ -155,6 +155,16 @@ def test_umma_selftest():
     assert 0.0 <= err.value < 1e-3, err.value
 
 
+def test_umma_ts_selftest():
+    """The same product with the A operand in tensor memory, written with tcgen05.st in the SpaceNet epilogue's layout
+    (SPACE_A_TMEM: activations never leave tensor memory between layers)."""
+    import ctypes
+    from stnerf_b200 import _lib as L
+    err = ctypes.c_float(-1.0)
+    L.check(L.lib().stnerf_selftest_umma_ts(ctypes.byref(err)), "stnerf_selftest_umma_ts")
+    assert 0.0 <= err.value < 1e-3, err.value
+
+
 @pytest.mark.gpu
 def test_umma_pair_selftest():
     """256x256x64 through ONE cta_group::2 accumulator: a 2-CTA cluster, each CTA holding its 128 rows of A and half of the B
