@@ -1,3 +1,4 @@
+# A/B recipe (variants: python -c "import __graft_entry__ as g; g.build_variant('hf', ['SPACE_A_TMEM=0']); g.build_variant('atmem4', ['SPACE_RING=4'])")
 # A/B of the tensor-memory activation path (SPACE_A_TMEM): bit comparison against the shared-memory build, then alternating benches
 set -x
 mkdir -p gpurun_out

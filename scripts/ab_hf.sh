@@ -1,3 +1,4 @@
+# A/B recipe of the HI-first hand-off: variant_base.so = the previous commit built with __graft_entry__.build_variant('base', []) in a worktree, copied next to the library
 set -x
 mkdir -p gpurun_out
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_hf.log 2>&1; echo smoke rc=$?
